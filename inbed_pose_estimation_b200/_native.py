@@ -1,0 +1,217 @@
+"""ctypes binding of libsmplify_b200.so (include/smplify_b200.h).
+
+The shared library is built in-tree by ``build()`` with nvcc for sm_100a and loaded with
+ctypes; torch only supplies device memory, the current stream and autograd plumbing.
+There is no fallback: if the library is missing and cannot be built, or no CUDA device
+is present when a model is created, the calls raise.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+
+from . import constants as C
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, 'csrc')
+LIB_PATH = os.path.join(_HERE, 'libsmplify_b200.so')
+SOURCES = ['kernels.cu', 'api.cu', 'model_host.cpp']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              '-shared', '-Xcompiler', '-fPIC']
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(os.path.dirname(_HERE), 'include', 'smplify_b200.h'))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a into the package directory."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError('nvcc not found: cannot build %s' % LIB_PATH)
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-o', LIB_PATH + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout)
+    os.replace(LIB_PATH + '.tmp', LIB_PATH)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [
+        ('v_template', _f32p), ('shapedirs', _f32p), ('posedirs', _f32p), ('J_regressor', _f32p),
+        ('weights', _f32p), ('J_regressor_extra', _f32p), ('parents', _i32p),
+        ('extra_vertex_ids', _i32p), ('joint_map', _i32p), ('ign_joints', _i32p),
+        ('num_ign_joints', ctypes.c_int32), ('cam_op_joints', _i32p), ('cam_gt_joints', _i32p),
+        ('angle_prior_ids', _i32p), ('angle_prior_signs', _f32p), ('gmm_means', _f32p),
+        ('gmm_precisions', _f32p), ('gmm_nll_weights', _f32p),
+    ]
+
+
+def make_desc(arrays, prior=None):
+    """(ModelDesc, keepalive list) from the numpy arrays of an SMPL model.
+
+    arrays: dict with v_template [6890,3], shapedirs [6890,3,10], posedirs [6890,3,207],
+            J_regressor [24,6890], weights [6890,24], J_regressor_extra [9,6890], parents [24].
+    prior:  None or dict with means [8,69], precisions [8,69,69], nll_weights [8] (fp32)."""
+    keep = []
+
+    def f32(a, shape):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError('expected shape %s, got %s' % (shape, a.shape))
+        keep.append(a)
+        return a.ctypes.data_as(_f32p)
+
+    def i32(a, n):
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+        if a.shape != (n,):
+            raise ValueError('expected %d int entries, got %s' % (n, a.shape))
+        keep.append(a)
+        return a.ctypes.data_as(_i32p)
+
+    V, J = C.NUM_VERTS, C.NUM_SMPL_JOINTS
+    d = ModelDesc()
+    d.v_template = f32(arrays['v_template'], (V, 3))
+    d.shapedirs = f32(arrays['shapedirs'], (V, 3, C.NUM_BETAS))
+    d.posedirs = f32(arrays['posedirs'], (V, 3, C.NUM_POSE_FEATURES))
+    d.J_regressor = f32(arrays['J_regressor'], (J, V))
+    d.weights = f32(arrays['weights'], (V, J))
+    d.J_regressor_extra = f32(arrays['J_regressor_extra'], (9, V))
+    parents = np.asarray(arrays['parents']).astype(np.int64).copy()
+    parents[0] = -1
+    d.parents = i32(parents, J)
+    d.extra_vertex_ids = i32(C.SMPL_EXTRA_VERTEX_IDS, 21)
+    d.joint_map = i32([C.JOINT_MAP[n] for n in C.JOINT_NAMES], C.NUM_JOINTS_OUT)
+    d.ign_joints = i32(C.SMPLIFY_IGNORED_JOINTS, len(C.SMPLIFY_IGNORED_JOINTS))
+    d.num_ign_joints = len(C.SMPLIFY_IGNORED_JOINTS)
+    d.cam_op_joints = i32(C.CAMERA_OP_JOINTS, 4)
+    d.cam_gt_joints = i32(C.CAMERA_GT_JOINTS, 4)
+    d.angle_prior_ids = i32(C.ANGLE_PRIOR_IDS, 4)
+    d.angle_prior_signs = f32(C.ANGLE_PRIOR_SIGNS, (4,))
+    if prior is not None:
+        d.gmm_means = f32(prior['means'], (8, 69))
+        d.gmm_precisions = f32(prior['precisions'], (8, 69, 69))
+        d.gmm_nll_weights = f32(np.asarray(prior['nll_weights']).reshape(-1), (8,))
+    return d, keep
+
+
+def _declare(lib):
+    vp, sz, ci, cf = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
+    lib.smplb200_version.restype = ci
+    lib.smplb200_last_error.restype = ctypes.c_char_p
+    lib.smplb200_launch_count.restype = ctypes.c_longlong
+    lib.smplb200_launch_count.argtypes = [ci]
+    lib.smplb200_model_create.restype = ci
+    lib.smplb200_model_create.argtypes = [ctypes.POINTER(ModelDesc), ci, ctypes.POINTER(vp)]
+    lib.smplb200_model_destroy.restype = None
+    lib.smplb200_model_destroy.argtypes = [vp]
+    for name in ('smplb200_fit_workspace_bytes', 'smplb200_smpl_workspace_bytes'):
+        getattr(lib, name).restype = sz
+        getattr(lib, name).argtypes = [ci]
+    lib.smplb200_smplify_fit.restype = ci
+    lib.smplb200_smplify_fit.argtypes = [vp, ci, ci, cf, cf] + [vp] * 12 + [vp, sz, vp]
+    lib.smplb200_smplify_fitting_loss.restype = ci
+    lib.smplb200_smplify_fitting_loss.argtypes = [vp, ci, cf] + [vp] * 6 + [vp, sz, vp]
+    lib.smplb200_smpl_forward.restype = ci
+    lib.smplb200_smpl_forward.argtypes = [vp, ci, ci] + [vp] * 5 + [vp, sz, vp]
+    lib.smplb200_smpl_backward.restype = ci
+    lib.smplb200_smpl_backward.argtypes = [vp, ci, ci] + [vp] * 7 + [vp, sz, vp]
+    lib.smplb200_batch_rodrigues.restype = ci
+    lib.smplb200_batch_rodrigues.argtypes = [ci, vp, vp, vp]
+    lib.smplb200_batch_rodrigues_backward.restype = ci
+    lib.smplb200_batch_rodrigues_backward.argtypes = [ci, vp, vp, vp, vp]
+    lib.smplb200_perspective_projection.restype = ci
+    lib.smplb200_perspective_projection.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp]
+    lib.smplb200_perspective_projection_backward.restype = ci
+    lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+    lib.smplb200_smplify_fit_host.restype = ci
+    lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    'smplb200_version', 'smplb200_last_error', 'smplb200_model_create', 'smplb200_model_destroy',
+    'smplb200_fit_workspace_bytes', 'smplb200_smpl_workspace_bytes', 'smplb200_smplify_fit',
+    'smplb200_smplify_fitting_loss', 'smplb200_smpl_forward', 'smplb200_smpl_backward',
+    'smplb200_batch_rodrigues', 'smplb200_batch_rodrigues_backward', 'smplb200_perspective_projection',
+    'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count',
+)
+
+
+def lib():
+    """The loaded library (built on first use when nvcc is available)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if _stale():
+                build()
+            _lib = _declare(ctypes.CDLL(LIB_PATH))
+        return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libsmplify_b200: ' + lib().smplb200_last_error().decode('utf-8', 'replace'))
+
+
+def ptr(t):
+    """Device (or host) address of a contiguous fp32 torch tensor / numpy array, or NULL."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        assert t.dtype == np.float32 and t.flags['C_CONTIGUOUS']
+        return ctypes.c_void_p(t.ctypes.data)
+    assert t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4, 'need contiguous fp32'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class NativeModel(object):
+    """Owner of one device-resident constant blob (smplb200_model)."""
+
+    def __init__(self, arrays, prior=None, device_index=0):
+        desc, keep = make_desc(arrays, prior)
+        handle = ctypes.c_void_p()
+        check(lib().smplb200_model_create(ctypes.byref(desc), int(device_index), ctypes.byref(handle)))
+        del keep
+        self.handle = handle
+        self.device_index = int(device_index)
+        self.has_prior = prior is not None
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            lib().smplb200_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

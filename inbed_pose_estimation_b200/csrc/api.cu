@@ -1,0 +1,353 @@
+// extern "C" boundary of libsmplify_b200.so (see include/smplify_b200.h).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/smplify_b200.h"
+#include "fit_driver.cuh"
+#include "launch.h"
+#include "model_host.h"
+
+using namespace smplb200;
+
+struct smplb200_model {
+    int device = 0;
+    ModelView view;
+    bool has_prior = false;
+    std::vector<void*> allocations;
+    // grow-only device scratch + pinned staging of the host-buffer entry point
+    std::mutex mu;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+static thread_local std::string g_error;
+static thread_local long long g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return 1;
+}
+#define CUDA_OK(expr)                                                                  \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(_e));   \
+    } while (0)
+
+extern "C" int smplb200_version(void) { return 100; }
+extern "C" const char* smplb200_last_error(void) { return g_error.c_str(); }
+extern "C" long long smplb200_launch_count(int reset) {
+    const long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+template <typename T>
+static int upload(smplb200_model* m, const std::vector<T>& h, const T** out) {
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, h.size() * sizeof(T)));
+    m->allocations.push_back(p);
+    CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return 0;
+}
+
+extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device, smplb200_model** out) {
+    if (!desc || !out) return fail("smplb200_model_create: NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("smplb200_model_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("smplb200_model_create: device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail("smplb200_model_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    HostModel H;
+    const std::string err = build_host_model(*desc, H);
+    if (!err.empty()) return fail("smplb200_model_create: %s", err.c_str());
+    CUDA_OK(cudaSetDevice(device));
+    smplb200_model* m = new smplb200_model();
+    m->device = device;
+    m->view = H.view;
+    m->has_prior = H.has_prior;
+    int rc = 0;
+    rc |= upload(m, H.basis, &m->view.basis);
+    rc |= upload(m, H.basisT, &m->view.basisT);
+    rc |= upload(m, H.weights, &m->view.weights);
+    rc |= upload(m, H.Cf, &m->view.Cf);
+    rc |= upload(m, H.CfT, &m->view.CfT);
+    rc |= upload(m, H.wkj, &m->view.wkj);
+    rc |= upload(m, H.Wp, &m->view.Wp);
+    rc |= upload(m, H.J0, &m->view.J0);
+    rc |= upload(m, H.JS, &m->view.JS);
+    rc |= upload(m, H.gmm_means, &m->view.gmm_means);
+    rc |= upload(m, H.gmm_prec, &m->view.gmm_prec);
+    rc |= upload(m, H.gmm_pmean, &m->view.gmm_pmean);
+    rc |= upload(m, H.gmm_lognll, &m->view.gmm_lognll);
+    if (rc) {
+        smplb200_model_destroy(m);
+        return 1;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void smplb200_model_destroy(smplb200_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (void* p : m->allocations) cudaFree(p);
+    if (m->scratch) cudaFree(m->scratch);
+    if (m->host_stream) cudaStreamDestroy(m->host_stream);
+    delete m;
+}
+
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+extern "C" size_t smplb200_fit_workspace_bytes(int batch) {
+    if (batch < 0) return 0;
+    return align256((size_t)batch * 288 * 4) + align256((size_t)batch * kXPad * 4) + 256;
+}
+extern "C" size_t smplb200_smpl_workspace_bytes(int batch) {
+    if (batch < 0) return 0;
+    return (size_t)(1 + kMaxSplit) * (align256((size_t)batch * 288 * 4) + align256((size_t)batch * kXPad * 4)) + 256;
+}
+
+static AdamConsts adam_consts(double beta1, double beta2) {
+    AdamConsts c;
+    c.lerp_w = (float)(1.0 - beta1);
+    c.beta2 = (float)beta2;
+    c.w2 = (float)(1.0 - beta2);
+    c.eps = 1e-8f;
+    return c;
+}
+
+static int run_fit(const smplb200_model* m, int batch, int num_iters, float step_size, float focal, int loss_only,
+                   const float* pose, const float* betas, const float* cam, const float* center, float* kp,
+                   float* vertices, float* joints, float* opose, float* obetas, float* ocam, float* reproj, float* trace,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!m) return fail("NULL model");
+    if (batch < 0) return fail("negative batch");
+    if (batch == 0) return 0;
+    if (!loss_only && !m->has_prior) return fail("smplify_fit: the model was created without a GMM prior");
+    if (num_iters < 0 || num_iters > kMaxIters) return fail("num_iters must be in [0, %d]", kMaxIters);
+    if (!pose || !betas || !cam || !center || !kp || !reproj) return fail("smplify: NULL required buffer");
+    if (ws_bytes < smplb200_fit_workspace_bytes(batch) || !ws) return fail("smplify: workspace too small");
+    char* w = static_cast<char*>(ws);
+    w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(w)));
+    float* ws_A = reinterpret_cast<float*>(w);
+    float* ws_x = reinterpret_cast<float*>(w + align256((size_t)batch * 288 * 4));
+    FitParams P;
+    memset(&P, 0, sizeof(P));
+    P.batch = batch;
+    P.num_iters = loss_only ? 0 : num_iters;
+    P.zero_conf_first = loss_only;
+    P.focal = focal;
+    P.init_pose = pose; P.init_betas = betas; P.init_cam = cam; P.center = center; P.keypoints = kp;
+    P.out_joints = joints; P.out_pose = opose; P.out_betas = obetas; P.out_cam = ocam; P.out_reproj = reproj;
+    P.ws_A = vertices ? ws_A : nullptr;
+    P.ws_x = vertices ? ws_x : nullptr;
+    P.loss_trace = trace;
+    P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
+    P.adam_c = adam_consts(P.beta1, P.beta2);
+    CUDA_OK(launch_fit(m->view, P, st));
+    ++g_launches;
+    if (vertices) {
+        CUDA_OK(launch_vertex_forward(m->view, ws_x, ws_A, vertices, nullptr, batch, st));
+        ++g_launches;
+    }
+    return 0;
+}
+
+extern "C" int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+                                    const float* init_pose, const float* init_betas, const float* init_cam_t,
+                                    const float* camera_center, float* keypoints_2d, float* vertices, float* joints,
+                                    float* pose, float* betas, float* camera_translation, float* reprojection_loss,
+                                    float* loss_trace, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!joints || !pose || !betas || !camera_translation) return fail("smplify_fit: NULL output buffer");
+    return run_fit(model, batch, num_iters, step_size, focal_length, 0, init_pose, init_betas, init_cam_t, camera_center,
+                   keypoints_2d, vertices, joints, pose, betas, camera_translation, reprojection_loss, loss_trace, workspace,
+                   workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int smplb200_smplify_fitting_loss(const smplb200_model* model, int batch, float focal_length, const float* pose,
+                                             const float* betas, const float* cam_t, const float* camera_center,
+                                             float* keypoints_2d, float* reprojection_loss, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+    return run_fit(model, batch, 0, 0.f, focal_length, 1, pose, betas, cam_t, camera_center, keypoints_2d, nullptr, nullptr,
+                   nullptr, nullptr, nullptr, reprojection_loss, nullptr, workspace, workspace_bytes,
+                   static_cast<cudaStream_t>(stream));
+}
+
+static void split_workspace(void* ws, int batch, float** A, float** x, float** dA, float** dx) {
+    char* w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(ws)));
+    const size_t a = align256((size_t)batch * 288 * 4), b = align256((size_t)batch * kXPad * 4);
+    *A = reinterpret_cast<float*>(w);
+    *x = reinterpret_cast<float*>(w + a);
+    *dA = reinterpret_cast<float*>(w + a + b);
+    *dx = reinterpret_cast<float*>(w + a + b + (size_t)kMaxSplit * a);
+}
+
+extern "C" int smplb200_smpl_forward(const smplb200_model* m, int batch, int rotmat_mode, const float* pose, const float* betas,
+                                     float* vertices, float* joints, float* saved_vposed, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (!m) return fail("NULL model");
+    if (batch < 0) return fail("negative batch");
+    if (batch == 0) return 0;
+    if (!pose || !betas) return fail("smpl_forward: NULL input");
+    if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_forward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *A, *x, *dA, *dx;
+    split_workspace(workspace, batch, &A, &x, &dA, &dx);
+    PoseParams P;
+    memset(&P, 0, sizeof(P));
+    P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas; P.joints = joints;
+    P.ws_A = A; P.ws_x = x;
+    CUDA_OK(launch_pose_forward(m->view, P, st));
+    ++g_launches;
+    if (vertices) {
+        CUDA_OK(launch_vertex_forward(m->view, x, A, vertices, saved_vposed, batch, st));
+        ++g_launches;
+    }
+    return 0;
+}
+
+extern "C" int smplb200_smpl_backward(const smplb200_model* m, int batch, int rotmat_mode, const float* pose, const float* betas,
+                                      const float* saved_vposed, const float* grad_vertices, const float* grad_joints,
+                                      float* grad_pose, float* grad_betas, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!m) return fail("NULL model");
+    if (batch < 0) return fail("negative batch");
+    if (batch == 0) return 0;
+    if (!pose || !betas || !grad_pose || !grad_betas) return fail("smpl_backward: NULL buffer");
+    if (grad_vertices && !saved_vposed) return fail("smpl_backward: grad_vertices needs saved_vposed from the forward call");
+    if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_backward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *A, *x, *dA, *dx;
+    split_workspace(workspace, batch, &A, &x, &dA, &dx);
+    PoseParams P;
+    memset(&P, 0, sizeof(P));
+    P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas;
+    int nsplit = 0;
+    if (grad_vertices) {
+        // A of the forward pass is recomputed (cheap) so that the backward call is self-contained.
+        PoseParams F = P;
+        F.ws_A = A;
+        CUDA_OK(launch_pose_forward(m->view, F, st));
+        ++g_launches;
+        const int tiles = (batch + 15) / 16;
+        nsplit = (2 * 148 + tiles - 1) / tiles;
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+        CUDA_OK(launch_vertex_backward(m->view, A, saved_vposed, grad_vertices, dA, dx, batch, nsplit, st));
+        ++g_launches;
+        P.dA_part = dA; P.dx_part = dx; P.nsplit = nsplit;
+    }
+    P.d_joints = grad_joints; P.d_pose = grad_pose; P.d_betas = grad_betas;
+    CUDA_OK(launch_pose_backward(m->view, P, st));
+    ++g_launches;
+    return 0;
+}
+
+extern "C" int smplb200_batch_rodrigues(int n, const float* theta, float* rotmat, void* stream) {
+    if (n < 0 || (n > 0 && (!theta || !rotmat))) return fail("batch_rodrigues: bad arguments");
+    CUDA_OK(launch_quat_rodrigues_fwd(theta, rotmat, n, static_cast<cudaStream_t>(stream)));
+    if (n) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_batch_rodrigues_backward(int n, const float* theta, const float* grad_rotmat, float* grad_theta, void* stream) {
+    if (n < 0 || (n > 0 && (!theta || !grad_rotmat || !grad_theta))) return fail("batch_rodrigues_backward: bad arguments");
+    CUDA_OK(launch_quat_rodrigues_bwd(theta, grad_rotmat, grad_theta, n, static_cast<cudaStream_t>(stream)));
+    if (n) ++g_launches;
+    return 0;
+}
+
+extern "C" int smplb200_perspective_projection(int batch, int num_points, const float* points, const float* rotation,
+                                               const float* translation, const float* focal_length, int focal_per_batch,
+                                               const float* camera_center, float* projected, void* stream) {
+    if (batch < 0 || num_points < 0) return fail("perspective_projection: negative size");
+    if ((size_t)batch * num_points == 0) return 0;
+    if (!points || !rotation || !translation || !focal_length || !camera_center || !projected)
+        return fail("perspective_projection: NULL buffer");
+    CUDA_OK(launch_projection_fwd(points, rotation, translation, focal_length, focal_per_batch, camera_center, projected, batch,
+                                  num_points, static_cast<cudaStream_t>(stream)));
+    ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_perspective_projection_backward(int batch, int num_points, const float* points, const float* rotation,
+                                                        const float* translation, const float* focal_length, int focal_per_batch,
+                                                        const float* grad_projected, float* grad_points, float* grad_rotation,
+                                                        float* grad_translation, void* stream) {
+    if (batch < 0 || num_points < 0) return fail("perspective_projection_backward: negative size");
+    if (batch == 0) return 0;
+    if (!points || !rotation || !translation || !focal_length || !grad_projected || !grad_points || !grad_rotation || !grad_translation)
+        return fail("perspective_projection_backward: NULL buffer");
+    CUDA_OK(launch_projection_bwd(points, rotation, translation, focal_length, focal_per_batch, grad_projected, grad_points,
+                                  grad_rotation, grad_translation, batch, num_points, static_cast<cudaStream_t>(stream)));
+    ++g_launches;
+    return 0;
+}
+
+// Host-buffer wrapper: H2D of the five inputs, fit, D2H of the results, synchronise.
+extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, int num_iters, float step_size, float focal_length,
+                                         const float* init_pose, const float* init_betas, const float* init_cam_t,
+                                         const float* camera_center, float* keypoints_2d, float* vertices, float* joints,
+                                         float* pose, float* betas, float* camera_translation, float* reprojection_loss) {
+    if (!cm) return fail("NULL model");
+    if (batch <= 0) return batch == 0 ? 0 : fail("negative batch");
+    smplb200_model* m = const_cast<smplb200_model*>(cm);
+    std::lock_guard<std::mutex> lock(m->mu);
+    CUDA_OK(cudaSetDevice(m->device));
+    if (!m->host_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
+    const size_t B = (size_t)batch;
+    const size_t n_in = B * (72 + 10 + 3 + 2 + 147), n_out = B * (147 + 72 + 10 + 3 + 49);
+    const size_t need = align256(n_in * 4) + align256(n_out * 4) + align256(B * kCols * 4) +
+                        smplb200_fit_workspace_bytes(batch) + 1024;
+    if (m->scratch_bytes < need) {
+        if (m->scratch) CUDA_OK(cudaFree(m->scratch));
+        m->scratch = nullptr;
+        m->scratch_bytes = 0;
+        CUDA_OK(cudaMalloc(&m->scratch, need));
+        m->scratch_bytes = need;
+    }
+    cudaStream_t st = m->host_stream;
+    char* base = static_cast<char*>(m->scratch);
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_pose = d_in; float* d_betas = d_pose + B * 72; float* d_cam = d_betas + B * 10;
+    float* d_cen = d_cam + B * 3; float* d_kp = d_cen + B * 2;
+    float* d_out = reinterpret_cast<float*>(base + align256(n_in * 4));
+    float* o_joints = d_out; float* o_pose = o_joints + B * 147; float* o_betas = o_pose + B * 72;
+    float* o_cam = o_betas + B * 10; float* o_reproj = o_cam + B * 3;
+    char* after = base + align256(n_in * 4) + align256(n_out * 4);
+    float* d_verts = reinterpret_cast<float*>(after);      // always computed, like the reference; copied back on request
+    after += align256(B * kCols * 4);
+    void* ws = after;
+    CUDA_OK(cudaMemcpyAsync(d_pose, init_pose, B * 72 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_betas, init_betas, B * 10 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_cam, init_cam_t, B * 3 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_cen, camera_center, B * 2 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(d_kp, keypoints_2d, B * 147 * 4, cudaMemcpyHostToDevice, st));
+    if (run_fit(m, batch, num_iters, step_size, focal_length, 0, d_pose, d_betas, d_cam, d_cen, d_kp, d_verts, o_joints, o_pose,
+                o_betas, o_cam, o_reproj, nullptr, ws, smplb200_fit_workspace_bytes(batch) + 512, st))
+        return 1;
+    CUDA_OK(cudaMemcpyAsync(joints, o_joints, B * 147 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(pose, o_pose, B * 72 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(betas, o_betas, B * 10 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(camera_translation, o_cam, B * 3 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(reprojection_loss, o_reproj, B * 49 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(keypoints_2d, d_kp, B * 147 * 4, cudaMemcpyDeviceToHost, st));   // in-place confidence zeroing
+    if (vertices) CUDA_OK(cudaMemcpyAsync(vertices, d_verts, B * kCols * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}

@@ -1,0 +1,392 @@
+// Tile-level drivers built from the phases in fit_tile.cuh:
+//   fit_tile            - SMPLify.__call__ (reference smplify/smplify.py:40-136) and get_fitting_loss (:138-172)
+//   pose_forward_tile   - the per-sample half of SMPL.forward (models/smpl.py:21-33): joints, A, x
+//   pose_backward_tile  - its gradient
+// They are __host__ __device__ so the TEST-ONLY emulation build can run them on the host.
+#pragma once
+#include "fit_tile.cuh"
+
+namespace smplb200 {
+
+struct FitParams {
+    int batch;
+    int num_iters;            // per stage; 0 => only the final forward (get_fitting_loss)
+    int zero_conf_first;      // get_fitting_loss zeroes the ignored confidences before anything else
+    float focal;
+    const float* init_pose;   // [B][72]
+    const float* init_betas;  // [B][10]
+    const float* init_cam;    // [B][3]
+    const float* center;      // [B][2]
+    float* keypoints;         // [B][49][3], confidences of the ignored joints are zeroed in place
+    float* out_joints;        // [B][49][3]  (nullable)
+    float* out_pose;          // [B][72]     (nullable)
+    float* out_betas;         // [B][10]     (nullable)
+    float* out_cam;           // [B][3]      (nullable)
+    float* out_reproj;        // [B][49]
+    float* ws_A;              // [B][24][12] (nullable) skinning transforms of the final pose for the vertex kernel
+    float* ws_x;              // [B][224]    (nullable) blend coefficients of the final pose
+    float* loss_trace;        // [2*num_iters][B] (nullable) per-sample loss of every iteration
+    double lr, beta1, beta2;  // Adam hyper-parameters (smplify.py:79,107: lr=step_size, betas=(0.9, 0.999))
+    AdamConsts adam_c;
+};
+
+constexpr float kSigma2 = 100.f * 100.f;              // gmof sigma (losses.py:28)
+constexpr float kPosePriorW2 = (float)(4.78 * 4.78);  // pose_prior_weight ** 2
+constexpr float kAnglePriorW2 = (float)(15.2 * 15.2); // angle_prior_weight ** 2
+constexpr float kShapePriorW2 = 25.f;                 // shape_prior_weight ** 2
+constexpr float kDepthW2 = 100.f * 100.f;             // depth_loss_weight ** 2 (losses.py:61)
+
+// forward through the folded joint model for the tile's current parameters
+template <int S>
+SB_HD void tile_forward(const ModelView& M, float* sm, bool from_axis_angle, bool root_identity) {
+    ph_pose_features<S>(sm, from_axis_angle, root_identity);
+    ph_rest_joints<S>(M, sm);
+    TILE_SYNC();
+    ph_chain_forward<S>(M, sm);           // ends with a barrier
+    ph_fold_gemm_forward<S>(M, sm);
+    TILE_SYNC();
+    ph_output_joints<S>(M, sm);
+    TILE_SYNC();
+}
+
+// Stage 1 (camera_fitting_loss, smplify.py:70-91): only the root rotation and the camera move, so all
+// 49 joints are an affine image of the root-identity pose:  joint = R0 (rest - sigma J0) + sigma J0.
+// One thread per sample runs the whole stage in registers.
+template <int S>
+SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    const AdamScalars* adam_tab = reinterpret_cast<const AdamScalars*>(sm + L::TOTAL);
+    FOR_ITEMS(s, S) {
+        const int b = tile * S + s;
+        float th[3], t[3], mm[6], vv[6];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { th[a] = sm[L::POSE + a * S + s]; t[a] = sm[L::CAM + a * S + s]; }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { mm[a] = 0.f; vv[a] = 0.f; }
+        const float tz0 = t[2];
+        const float cx = sm[L::CEN + 0 * S + s], cy = sm[L::CEN + 1 * S + s];
+        float cmin = sm[L::KP + (3 * M.cam_op[0] + 2) * S + s];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) cmin = fminf(cmin, sm[L::KP + (3 * M.cam_op[q] + 2) * S + s]);
+        const bool use_op = cmin > 0.f;                       // losses.py:83
+        const float J0[3] = {sm[L::JR + 0 * S + s], sm[L::JR + 1 * S + s], sm[L::JR + 2 * S + s]};
+        float av[4][3], bv[4][3], kx[4], ky[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = use_op ? M.cam_op[q] : M.cam_gt[q];
+            const float sig = M.sigma_src[M.joint_map[o]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                bv[q][c] = sig * J0[c];
+                av[q][c] = sm[L::OUTJ + (3 * o + c) * S + s] - bv[q][c];
+            }
+            kx[q] = sm[L::KP + (3 * o + 0) * S + s];
+            ky[q] = sm[L::KP + (3 * o + 1) * S + s];
+        }
+        for (int it = 0; it < P.num_iters; ++it) {
+            float R[9], dR[9], dt[3] = {0.f, 0.f, 0.f};
+            rodrigues_fwd(th[0], th[1], th[2], R);
+#pragma unroll
+            for (int e = 0; e < 9; ++e) dR[e] = 0.f;
+            float loss = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float Pw[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    Pw[r] = ((R[r * 3 + 0] * av[q][0] + R[r * 3 + 1] * av[q][1] + R[r * 3 + 2] * av[q][2]) + bv[q][r]) + t[r];
+                const float px = Pw[0] / Pw[2], py = Pw[1] / Pw[2];
+                const float ex = kx[q] - (P.focal * px + cx), ey = ky[q] - (P.focal * py + cy);
+                loss += ex * ex + ey * ey;
+                const float gu = -2.f * ex * P.focal, gv = -2.f * ey * P.focal;
+                const float dP[3] = {gu / Pw[2], gv / Pw[2], -(gu * px + gv * py) / Pw[2]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    dR[r * 3 + 0] += dP[r] * av[q][0]; dR[r * 3 + 1] += dP[r] * av[q][1]; dR[r * 3 + 2] += dP[r] * av[q][2];
+                    dt[r] += dP[r];
+                }
+            }
+            const float dz = t[2] - tz0;
+            loss += kDepthW2 * (dz * dz);
+            dt[2] += 2.f * kDepthW2 * dz;
+            if (P.loss_trace && b < P.batch) P.loss_trace[(size_t)it * P.batch + b] = loss;
+            float dth[3];
+            rodrigues_bwd(th[0], th[1], th[2], dR, dth);
+            const AdamScalars sc = adam_tab[it];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                th[a] = adam_update(th[a], dth[a], mm[a], vv[a], P.adam_c, sc);
+                t[a] = adam_update(t[a], dt[a], mm[3 + a], vv[3 + a], P.adam_c, sc);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { sm[L::POSE + a * S + s] = th[a]; sm[L::CAM + a * S + s] = t[a]; }
+    }
+}
+
+template <int S>
+SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, M.num_ign * S) {
+        const int s = it % S, o = M.ign_joints[it / S], b = tile * S + s;
+        sm[L::KP + (3 * o + 2) * S + s] = 0.f;
+        if (b < P.batch) P.keypoints[((size_t)b * kOut + o) * 3 + 2] = 0.f;   // in place, smplify.py:105 / :156
+    }
+}
+
+template <int S>
+SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    // per-iteration Adam scalars, computed in float64 like torch does on the host
+    AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::TOTAL);
+    FOR_ITEMS(t, P.num_iters) {
+        const double bc1 = 1.0 - pow(P.beta1, (double)(t + 1));
+        const double bc2 = 1.0 - pow(P.beta2, (double)(t + 1));
+        adam_tab[t].step_size = (float)(P.lr / bc1);
+        adam_tab[t].bc2_sqrt = (float)sqrt(bc2);
+    }
+    // ---- load the tile ---------------------------------------------------------------------
+    FOR_ITEMS(it, S * 72) {
+        const int s = it / 72, k = it % 72, b = tile * S + s;
+        sm[L::POSE + k * S + s] = (b < P.batch) ? P.init_pose[(size_t)b * 72 + k] : 0.f;
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        sm[L::BETA + k * S + s] = (b < P.batch) ? P.init_betas[(size_t)b * kBetas + k] : 0.f;
+    }
+    FOR_ITEMS(it, S * 3) {
+        const int s = it / 3, k = it % 3, b = tile * S + s;
+        sm[L::CAM + k * S + s] = (b < P.batch) ? P.init_cam[(size_t)b * 3 + k] : (k == 2 ? 1.f : 0.f);
+    }
+    FOR_ITEMS(it, S * 2) {
+        const int s = it / 2, k = it % 2, b = tile * S + s;
+        sm[L::CEN + k * S + s] = (b < P.batch) ? P.center[(size_t)b * 2 + k] : 0.f;
+    }
+    FOR_ITEMS(it, S * 147) {
+        const int s = it / 147, k = it % 147, b = tile * S + s;
+        sm[L::KP + k * S + s] = (b < P.batch) ? P.keypoints[(size_t)b * 147 + k] : 0.f;
+    }
+    TILE_SYNC();
+    if (P.zero_conf_first) { tile_zero_ignored_conf<S>(M, P, tile, sm); TILE_SYNC(); }
+
+    if (P.num_iters > 0) {
+        // ---- stage 1: global orientation + camera translation --------------------------------
+        tile_forward<S>(M, sm, true, /*root_identity=*/true);
+        stage1_camera<S>(M, P, tile, sm);
+        TILE_SYNC();
+        tile_zero_ignored_conf<S>(M, P, tile, sm);
+        zero_rows<S>(sm, L::ADM, 2 * kParams);
+        TILE_SYNC();
+
+        // ---- stage 2: body pose, betas, global orientation (body_fitting_loss) ----------------
+        for (int it = 0; it < P.num_iters; ++it) {
+            ph_prior_quadratic<S>(M, sm);
+            TILE_SYNC();
+            ph_prior_select<S>(M, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, M.angle_ids, M.angle_signs);
+            TILE_SYNC();
+            tile_forward<S>(M, sm, true, false);
+            ph_reprojection<S>(sm, P.focal, kSigma2, true);
+            zero_rows<S>(sm, L::DG, 288);
+            TILE_SYNC();
+            if (P.loss_trace) {
+                FOR_ITEMS(s, S) {
+                    const int b = tile * S + s;
+                    float a = 0.f;
+                    for (int o = 0; o < kOut; ++o) a += sm[L::LOSSJ + o * S + s];
+                    a = ((a + sm[L::LOSSJ + 49 * S + s]) + sm[L::LOSSJ + 50 * S + s]) + sm[L::LOSSJ + 51 * S + s];
+                    if (b < P.batch) P.loss_trace[(size_t)(P.num_iters + it) * P.batch + b] = a;
+                }
+            }
+            ph_joint_backward<S>(M, sm);
+            TILE_SYNC();
+            ph_pick_backward<S>(M, sm);
+            TILE_SYNC();
+            ph_fold_gemm_backward<S>(M, sm);
+            TILE_SYNC();
+            ph_chain_backward<S>(M, sm);
+            TILE_SYNC();
+            const AdamScalars sc = adam_tab[it];
+            FOR_ITEMS(itj, kJoints * S) {
+                const int s = itj % S, j = itj / S;
+                float g[9], d[3];
+                rotation_grad<S>(sm, j, s, g);
+                rodrigues_bwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
+                              sm[L::POSE + (3 * j + 2) * S + s], g, d);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int k = 3 * j + a;
+                    if (j > 0) d[a] += sm[L::GPR + (k - 3) * S + s];
+                    sm[L::POSE + k * S + s] = adam_update(sm[L::POSE + k * S + s], d[a], sm[L::ADM + k * S + s],
+                                                          sm[L::ADV + k * S + s], P.adam_c, sc);
+                }
+            }
+            FOR_ITEMS(itb, kBetas * S) {
+                const int s = itb % S, l = itb / S;
+                const float beta = sm[L::BETA + l * S + s];
+                const float g = beta_grad<S>(M, sm, l, s) + 2.f * kShapePriorW2 * beta;
+                sm[L::BETA + l * S + s] = adam_update(beta, g, sm[L::ADM + (72 + l) * S + s], sm[L::ADV + (72 + l) * S + s],
+                                                      P.adam_c, sc);
+            }
+            TILE_SYNC();
+        }
+    }
+
+    // ---- final forward: joints, per-joint reprojection loss, A and x for the vertex kernel --------
+    tile_forward<S>(M, sm, true, false);
+    FOR_ITEMS(it, S * 147) {
+        const int s = it / 147, k = it % 147, b = tile * S + s;
+        if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
+    }
+    FOR_ITEMS(it, S * kXPad) {
+        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+        if (P.ws_x && b < P.batch) P.ws_x[(size_t)b * kXPad + k] = sm[L::XT + k * S + s];
+    }
+    FOR_ITEMS(it, S * 288) {
+        const int s = it / 288, k = it % 288, b = tile * S + s;
+        const int j = k / 12, e = k % 12;
+        if (P.ws_A && b < P.batch)
+            P.ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
+    }
+    TILE_SYNC();
+    ph_reprojection<S>(sm, P.focal, kSigma2, false);
+    TILE_SYNC();
+    FOR_ITEMS(it, S * kOut) {
+        const int s = it / kOut, o = it % kOut, b = tile * S + s;
+        if (b < P.batch) P.out_reproj[(size_t)b * kOut + o] = sm[L::LOSSJ + o * S + s];
+    }
+    FOR_ITEMS(it, S * 72) {
+        const int s = it / 72, k = it % 72, b = tile * S + s;
+        if (P.out_pose && b < P.batch) P.out_pose[(size_t)b * 72 + k] = sm[L::POSE + k * S + s];
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        if (P.out_betas && b < P.batch) P.out_betas[(size_t)b * kBetas + k] = sm[L::BETA + k * S + s];
+    }
+    FOR_ITEMS(it, S * 3) {
+        const int s = it / 3, k = it % 3, b = tile * S + s;
+        if (P.out_cam && b < P.batch) P.out_cam[(size_t)b * 3 + k] = sm[L::CAM + k * S + s];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// SMPL.forward / backward, per-sample half
+// --------------------------------------------------------------------------------------------------
+struct PoseParams {
+    int batch;
+    int rotmat_mode;          // 0: pose is axis-angle [B][72]; 1: rotation matrices [B][24][9]
+    const float* pose;
+    const float* betas;       // [B][10]
+    float* joints;            // [B][49][3]
+    float* ws_A;              // [B][24][12]
+    float* ws_x;              // [B][224]
+    // backward only
+    const float* d_joints;    // [B][49][3] (nullable)
+    const float* dA_part;     // [nsplit][B][288] (nullable) from the vertex backward kernel
+    const float* dx_part;     // [nsplit][B][224] (nullable)
+    int nsplit;
+    float* d_pose;            // [B][72] or [B][24][9]
+    float* d_betas;           // [B][10]
+};
+
+template <int S>
+SB_HD void pose_load(const PoseParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    if (P.rotmat_mode) {
+        FOR_ITEMS(it, S * 216) {
+            const int s = it / 216, k = it % 216, b = tile * S + s;
+            sm[L::RM + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 216 + k] : ((k % 9) % 4 == 0 ? 1.f : 0.f);
+        }
+    } else {
+        FOR_ITEMS(it, S * 72) {
+            const int s = it / 72, k = it % 72, b = tile * S + s;
+            sm[L::POSE + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 72 + k] : 0.f;
+        }
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        sm[L::BETA + k * S + s] = (b < P.batch) ? P.betas[(size_t)b * kBetas + k] : 0.f;
+    }
+    TILE_SYNC();
+}
+
+template <int S>
+SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    pose_load<S>(P, tile, sm);
+    tile_forward<S>(M, sm, !P.rotmat_mode, false);
+    FOR_ITEMS(it, S * 147) {
+        const int s = it / 147, k = it % 147, b = tile * S + s;
+        if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
+    }
+    FOR_ITEMS(it, S * kXPad) {
+        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+        if (P.ws_x && b < P.batch) P.ws_x[(size_t)b * kXPad + k] = sm[L::XT + k * S + s];
+    }
+    FOR_ITEMS(it, S * 288) {
+        const int s = it / 288, k = it % 288, b = tile * S + s;
+        const int j = k / 12, e = k % 12;
+        if (P.ws_A && b < P.batch)
+            P.ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
+    }
+}
+
+template <int S>
+SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
+    using L = TileLayout<S>;
+    pose_load<S>(P, tile, sm);
+    tile_forward<S>(M, sm, !P.rotmat_mode, false);
+    FOR_ITEMS(it, S * 147) {
+        const int s = it / 147, k = it % 147, b = tile * S + s;
+        sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
+    }
+    FOR_ITEMS(it, S * 288) {
+        const int s = it / 288, k = it % 288, b = tile * S + s;
+        float a = 0.f;
+        if (P.dA_part && b < P.batch)
+            for (int sp = 0; sp < P.nsplit; ++sp) a += P.dA_part[((size_t)sp * P.batch + b) * 288 + k];
+        sm[L::DG + k * S + s] = a;
+    }
+    TILE_SYNC();
+    ph_joint_backward<S>(M, sm);
+    TILE_SYNC();
+    ph_pick_backward<S>(M, sm);
+    TILE_SYNC();
+    ph_fold_gemm_backward<S>(M, sm);
+    TILE_SYNC();
+    if (P.dx_part) {
+        FOR_ITEMS(it, S * kXPad) {
+            const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+            if (b < P.batch) {
+                float a = sm[L::XT + k * S + s];
+                for (int sp = 0; sp < P.nsplit; ++sp) a += P.dx_part[((size_t)sp * P.batch + b) * kXPad + k];
+                sm[L::XT + k * S + s] = a;
+            }
+        }
+        TILE_SYNC();
+    }
+    ph_chain_backward<S>(M, sm);
+    TILE_SYNC();
+    FOR_ITEMS(it, kJoints * S) {
+        const int s = it % S, j = it / S, b = tile * S + s;
+        float g[9];
+        rotation_grad<S>(sm, j, s, g);
+        if (b >= P.batch) continue;
+        if (P.rotmat_mode) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) P.d_pose[(size_t)b * 216 + j * 9 + e] = g[e];
+        } else {
+            float d[3];
+            rodrigues_bwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
+                          sm[L::POSE + (3 * j + 2) * S + s], g, d);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) P.d_pose[(size_t)b * 72 + 3 * j + a] = d[a];
+        }
+    }
+    FOR_ITEMS(it, kBetas * S) {
+        const int s = it % S, l = it / S, b = tile * S + s;
+        const float g = beta_grad<S>(M, sm, l, s);
+        if (b < P.batch) P.d_betas[(size_t)b * kBetas + l] = g;
+    }
+}
+
+}  // namespace smplb200

@@ -1,0 +1,654 @@
+// Per-tile (S samples per CTA) phases of the folded SMPL joint model, its backward pass,
+// the SMPLify losses and the Adam update.  Every phase is a parallel-for over "items"
+// followed by a block barrier; all cross-phase state lives in the tile's shared memory
+// ([index][S] layout, sample fastest, so lanes of a warp touch consecutive words).
+//
+// Reference semantics restated here (paths into /root/reference, smplx rows per SURVEY.md §8a):
+//   a8  smplx batch_rodrigues          -> rodrigues_fwd / rodrigues_bwd
+//   a9  pose_feature = R[1:] - I       -> ph_pose_features
+//   a7  J = J_regressor . v_shaped     -> ph_rest_joints   (folded: J0 + JS.beta)
+//   a10 batch_rigid_transform          -> ph_chain_forward / ph_chain_backward
+//   a11/a12/a5 skinning + joint regressors + joint_map -> folded GEMM (Cf) + ph_joint_*
+//   a13 perspective_projection, a14 gmof, a16 body_fitting_loss (smplify/losses.py:26-58)
+//   a17 camera_fitting_loss (losses.py:60-90), a19 MaxMixturePrior (prior.py:181-196)
+//   a15 angle_prior (losses.py:19-24), a20 torch.optim.Adam (_single_tensor_adam)
+#pragma once
+#include <math.h>
+#include "smpl_common.h"
+
+namespace smplb200 {
+
+#if defined(__CUDA_ARCH__)
+#define TILE_TID ((int)threadIdx.x)
+#define TILE_NT ((int)blockDim.x)
+#define TILE_SYNC() __syncthreads()
+#else
+#define TILE_TID 0
+#define TILE_NT 1
+#define TILE_SYNC() ((void)0)
+#endif
+#define FOR_ITEMS(it, n) for (int it = TILE_TID; it < (n); it += TILE_NT)
+
+template <int S>
+struct TileLayout {
+    static constexpr int LDQ = S + 4;               // padded row of QT: conflict-free 16-byte column stores
+    static constexpr int POSE = 0;                  // [72][S]
+    static constexpr int BETA = POSE + 72 * S;      // [10][S]
+    static constexpr int CAM = BETA + 10 * S;       // [3][S]
+    static constexpr int CEN = CAM + 3 * S;         // [2][S]
+    static constexpr int KP = CEN + 2 * S;          // [147][S]   (x, y, conf) per output joint
+    static constexpr int RM = KP + 147 * S;         // [216][S]   rotations; reused for dL/dR
+    static constexpr int XT = RM + 216 * S;         // [224][S]   x = [1, beta, feat]; reused for dL/dx
+    static constexpr int JR = XT + kXPad * S;       // [72][S]    rest joints
+    static constexpr int GW = JR + 72 * S;          // [288][S]   world transforms (3x4 row-major)
+    static constexpr int AT = GW + 288 * S;         // [72][S]    A_j translation column
+    static constexpr int QT = AT + 72 * S;          // [704][LDQ] folded GEMM output; reused for dL/dQ and prior scratch
+    static constexpr int OUTJ = QT + kQPad * LDQ;   // [147][S]   output joints; reused for dL/djoints
+    static constexpr int DG = OUTJ + 147 * S;       // [288][S]
+    static constexpr int DJ = DG + 288 * S;         // [72][S]
+    static constexpr int GPR = DJ + 72 * S;         // [69][S]    prior gradient w.r.t. body pose
+    static constexpr int LOSSJ = GPR + 69 * S;      // [52][S]    49 reprojection terms, gmm, angle, shape
+    static constexpr int ADM = LOSSJ + 52 * S;      // [82][S]
+    static constexpr int ADV = ADM + 82 * S;        // [82][S]
+    static constexpr int MISC = ADV + 82 * S;       // [16][S]
+    static constexpr int TOTAL = MISC + 16 * S;
+    static_assert(kGauss * kPriorDim * S <= kQPad * LDQ, "prior scratch must fit in the QT region");
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+// smplx.lbs.batch_rodrigues for one joint: angle = |r + 1e-8|, n = r / angle,
+// R = (I + sin K) + (1 - cos) K K.
+SB_HD void rodrigues_fwd(float rx, float ry, float rz, float* R) {
+    const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
+    const float ang = sqrtf(ax * ax + ay * ay + az * az);
+    const float nx = rx / ang, ny = ry / ang, nz = rz / ang;
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    const float oc = 1.0f - cs;
+    // K = [[0,-nz,ny],[nz,0,-nx],[-ny,nx,0]];  KK = K*K
+    const float kk00 = -nz * nz - ny * ny, kk01 = nx * ny, kk02 = nx * nz;
+    const float kk11 = -nz * nz - nx * nx, kk12 = ny * nz, kk22 = -ny * ny - nx * nx;
+    R[0] = 1.0f + oc * kk00;
+    R[1] = (-sn * nz) + oc * kk01;
+    R[2] = (sn * ny) + oc * kk02;
+    R[3] = (sn * nz) + oc * kk01;
+    R[4] = 1.0f + oc * kk11;
+    R[5] = (-sn * nx) + oc * kk12;
+    R[6] = (-sn * ny) + oc * kk02;
+    R[7] = (sn * nx) + oc * kk12;
+    R[8] = 1.0f + oc * kk22;
+}
+
+// Gradient of the map above: g = dL/dR (row-major 3x3) -> dL/dr.
+SB_HD void rodrigues_bwd(float rx, float ry, float rz, const float* g, float* dr) {
+    const float ax = rx + 1e-8f, ay = ry + 1e-8f, az = rz + 1e-8f;
+    const float ang = sqrtf(ax * ax + ay * ay + az * az);
+    const float inv = 1.0f / ang;
+    const float nx = rx / ang, ny = ry / ang, nz = rz / ang;
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+    const float oc = 1.0f - cs;
+    const float K[9] = {0.f, -nz, ny, nz, 0.f, -nx, -ny, nx, 0.f};
+    const float KK[9] = {-nz * nz - ny * ny, nx * ny, nx * nz,
+                         nx * ny, -nz * nz - nx * nx, ny * nz,
+                         nx * nz, ny * nz, -ny * ny - nx * nx};
+    float d_sin = 0.f, d_oc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+        d_sin += g[e] * K[e];
+        d_oc += g[e] * KK[e];
+    }
+    // dK = sin * g + (1-cos) * (g K^T + K^T g)
+    float dK[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) a += g[r * 3 + k] * K[c * 3 + k] + K[k * 3 + r] * g[k * 3 + c];
+            dK[r * 3 + c] = sn * g[r * 3 + c] + oc * a;
+        }
+    const float dnx = dK[7] - dK[5], dny = dK[2] - dK[6], dnz = dK[3] - dK[1];
+    float d_ang = d_sin * cs + d_oc * sn;
+    d_ang -= (dnx * rx + dny * ry + dnz * rz) * inv * inv;
+    dr[0] = dnx * inv + d_ang * ax * inv;
+    dr[1] = dny * inv + d_ang * ay * inv;
+    dr[2] = dnz * inv + d_ang * az * inv;
+}
+
+// Geman-McClure (losses.py:11-17) and its derivative.
+SB_HD float gmof_val(float x, float sigma2) { const float x2 = x * x; return (sigma2 * x2) / (sigma2 + x2); }
+SB_HD float gmof_grad(float x, float sigma2) { const float d = sigma2 + x * x; return (2.0f * sigma2 * sigma2 * x) / (d * d); }
+
+struct AdamConsts { float lerp_w, beta2, w2, eps; };
+
+// torch.optim.Adam single-tensor step, fp32 (adam.py _single_tensor_adam).
+SB_HD float adam_update(float p, float g, float& m, float& v, const AdamConsts& c, const AdamScalars& t) {
+    m = m + c.lerp_w * (g - m);
+    v = v * c.beta2;
+    v = v + (c.w2 * g) * g;
+    const float denom = sqrtf(v) / t.bc2_sqrt + c.eps;
+    return p + (-t.step_size) * (m / denom);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward phases
+// ------------------------------------------------------------------------------------------------
+// Rotations of all joints from axis-angle + pose features / betas into x.  root_identity forces
+// R_0 = I (stage-1 hoisting: the rest pose every root rotation is applied to).
+template <int S>
+SB_HD void ph_pose_features(float* sm, bool from_axis_angle, bool root_identity) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kJoints * S) {
+        const int s = it % S, j = it / S;
+        float R[9];
+        if (from_axis_angle) {
+            rodrigues_fwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
+                          sm[L::POSE + (3 * j + 2) * S + s], R);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R[e] = sm[L::RM + (j * 9 + e) * S + s];
+        }
+        if (j == 0 && root_identity) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R[e] = (e % 4 == 0) ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+            sm[L::RM + (j * 9 + e) * S + s] = R[e];
+            if (j > 0) sm[L::XT + (11 + (j - 1) * 9 + e) * S + s] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+        }
+    }
+    FOR_ITEMS(it, (1 + kBetas + (kXPad - kX)) * S) {
+        const int s = it % S, r = it / S;
+        if (r == 0) sm[L::XT + s] = 1.f;
+        else if (r <= kBetas) sm[L::XT + r * S + s] = sm[L::BETA + (r - 1) * S + s];
+        else sm[L::XT + (kX + r - 1 - kBetas) * S + s] = 0.f;
+    }
+}
+
+// J = J0 + JS.beta  (== J_regressor.(v_template + shapedirs.beta), folded in float64 at model creation)
+template <int S>
+SB_HD void ph_rest_joints(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, 72 * S) {
+        const int s = it % S, jc = it / S;
+        float a = M.J0[jc];
+#pragma unroll
+        for (int l = 0; l < kBetas; ++l) a += M.JS[jc * kBetas + l] * sm[L::BETA + l * S + s];
+        sm[L::JR + jc * S + s] = a;
+    }
+}
+
+// World transforms level by level; also A_j^t = G_j^t - G_j^R J_j.
+template <int S>
+SB_HD void ph_chain_forward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    for (int lev = 0; lev < M.num_levels; ++lev) {
+        const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
+        FOR_ITEMS(it, cnt * S) {
+            const int s = it % S, j = M.level_order[first + it / S], p = M.parents[j];
+            float G[12];
+            const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s],
+                        Jz = sm[L::JR + (3 * j + 2) * S + s];
+            if (p < 0) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) G[r * 4 + c] = sm[L::RM + (j * 9 + r * 3 + c) * S + s];
+                }
+                G[3] = Jx; G[7] = Jy; G[11] = Jz;
+            } else {
+                float Rl[9], Gp[12];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Rl[e] = sm[L::RM + (j * 9 + e) * S + s];
+#pragma unroll
+                for (int e = 0; e < 12; ++e) Gp[e] = sm[L::GW + (p * 12 + e) * S + s];
+                const float dx = Jx - sm[L::JR + (3 * p + 0) * S + s], dy = Jy - sm[L::JR + (3 * p + 1) * S + s],
+                            dz = Jz - sm[L::JR + (3 * p + 2) * S + s];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        G[r * 4 + c] = Gp[r * 4 + 0] * Rl[c] + Gp[r * 4 + 1] * Rl[3 + c] + Gp[r * 4 + 2] * Rl[6 + c];
+                    G[r * 4 + 3] = Gp[r * 4 + 0] * dx + Gp[r * 4 + 1] * dy + Gp[r * 4 + 2] * dz + Gp[r * 4 + 3];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) sm[L::GW + (j * 12 + e) * S + s] = G[e];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                sm[L::AT + (3 * j + r) * S + s] = G[r * 4 + 3] - (G[r * 4 + 0] * Jx + G[r * 4 + 1] * Jy + G[r * 4 + 2] * Jz);
+        }
+        TILE_SYNC();
+    }
+}
+
+// QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
+template <int S>
+SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    static_assert(S % 4 == 0, "S must be a multiple of 4");
+    FOR_ITEMS(n, kQ) {
+        float acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+        const float* cf = M.Cf + n;
+#pragma unroll 4
+        for (int m = 0; m < kX; ++m) {
+            const float c = cf[m * kQPad];
+            const float4* xr = reinterpret_cast<const float4*>(sm + L::XT + m * S);
+#pragma unroll
+            for (int q = 0; q < S / 4; ++q) {
+                const float4 xv = xr[q];
+                acc[4 * q + 0] += c * xv.x; acc[4 * q + 1] += c * xv.y;
+                acc[4 * q + 2] += c * xv.z; acc[4 * q + 3] += c * xv.w;
+            }
+        }
+        float4* qo = reinterpret_cast<float4*>(sm + L::QT + n * L::LDQ);
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) qo[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+}
+
+// dx[m][s] = sum_n Cf[m][n] * dQ[n][s]   (transpose GEMM; result overwrites XT)
+template <int S>
+SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    constexpr int H = (S % 8 == 0) ? 2 : 1;    // sample halves per row of x
+    constexpr int SH = S / H;
+    FOR_ITEMS(it, kXPad * H) {
+        const int m = it % kXPad, h = it / kXPad;
+        float acc[SH];
+#pragma unroll
+        for (int s = 0; s < SH; ++s) acc[s] = 0.f;
+        const float* ct = M.CfT + m;
+#pragma unroll 4
+        for (int n = 0; n < kQ; ++n) {
+            const float c = ct[n * kXPad];
+            const float4* qr = reinterpret_cast<const float4*>(sm + L::QT + n * L::LDQ + h * SH);
+#pragma unroll
+            for (int q = 0; q < SH / 4; ++q) {
+                const float4 v = qr[q];
+                acc[4 * q + 0] += c * v.x; acc[4 * q + 1] += c * v.y;
+                acc[4 * q + 2] += c * v.z; acc[4 * q + 3] += c * v.w;
+            }
+        }
+        float4* xo = reinterpret_cast<float4*>(sm + L::XT + m * S + h * SH);
+#pragma unroll
+        for (int q = 0; q < SH / 4; ++q) xo[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+}
+
+// One of the 54 source joints of sample s (chain joint, skinned picked vertex, folded extra joint).
+template <int S>
+SB_HD void source_joint(const ModelView& M, const float* sm, int src, int s, float* P) {
+    using L = TileLayout<S>;
+    if (src < kJoints) {
+        P[0] = sm[L::GW + (src * 12 + 3) * S + s];
+        P[1] = sm[L::GW + (src * 12 + 7) * S + s];
+        P[2] = sm[L::GW + (src * 12 + 11) * S + s];
+    } else if (src < kJoints + kSelVerts) {
+        const int p = src - kJoints;                    // only p < kPicks is ever requested
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        for (int j = 0; j < kJoints; ++j) {
+            const float w = M.Wp[p * kJoints + j];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[r * 4 + c] += w * sm[L::GW + (j * 12 + r * 4 + c) * S + s];
+                T[r * 4 + 3] += w * sm[L::AT + (3 * j + r) * S + s];
+            }
+        }
+        const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
+                    vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) P[r] = T[r * 4 + 0] * vx + T[r * 4 + 1] * vy + T[r * 4 + 2] * vz + T[r * 4 + 3];
+    } else {
+        const int k = src - (kJoints + kSelVerts);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int j = 0; j < kJoints; ++j) {
+            const int qb = (k * kJoints + j) * 3;
+            const float qx = sm[L::QT + (qb + 0) * L::LDQ + s], qy = sm[L::QT + (qb + 1) * L::LDQ + s], qz = sm[L::QT + (qb + 2) * L::LDQ + s];
+            const float w = M.wkj[k * kJoints + j];
+            const float* G = sm + L::GW + (j * 12) * S + s;
+            a0 += G[0 * S] * qx + G[1 * S] * qy + G[2 * S] * qz + sm[L::AT + (3 * j + 0) * S + s] * w;
+            a1 += G[4 * S] * qx + G[5 * S] * qy + G[6 * S] * qz + sm[L::AT + (3 * j + 1) * S + s] * w;
+            a2 += G[8 * S] * qx + G[9 * S] * qy + G[10 * S] * qz + sm[L::AT + (3 * j + 2) * S + s] * w;
+        }
+        P[0] = a0; P[1] = a1; P[2] = a2;
+    }
+}
+
+// The 49 output joints into OUTJ.
+template <int S>
+SB_HD void ph_output_joints(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kOut * S) {
+        const int s = it % S, o = it / S;
+        float P[3];
+        source_joint<S>(M, sm, M.joint_map[o], s, P);
+        sm[L::OUTJ + (3 * o + 0) * S + s] = P[0];
+        sm[L::OUTJ + (3 * o + 1) * S + s] = P[1];
+        sm[L::OUTJ + (3 * o + 2) * S + s] = P[2];
+    }
+}
+
+// Reprojection term of body_fitting_loss per output joint; with_grad also overwrites OUTJ with
+// dL/djoint.  LOSSJ[o] = conf^2 * (gmof(u - kx) + gmof(v - ky)).
+template <int S>
+SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kOut * S) {
+        const int s = it % S, o = it / S;
+        const float Px = sm[L::OUTJ + (3 * o + 0) * S + s] + sm[L::CAM + 0 * S + s];
+        const float Py = sm[L::OUTJ + (3 * o + 1) * S + s] + sm[L::CAM + 1 * S + s];
+        const float Pz = sm[L::OUTJ + (3 * o + 2) * S + s] + sm[L::CAM + 2 * S + s];
+        const float px = Px / Pz, py = Py / Pz;
+        const float du = (focal * px + sm[L::CEN + 0 * S + s]) - sm[L::KP + (3 * o + 0) * S + s];
+        const float dv = (focal * py + sm[L::CEN + 1 * S + s]) - sm[L::KP + (3 * o + 1) * S + s];
+        const float conf = sm[L::KP + (3 * o + 2) * S + s];
+        const float c2 = conf * conf;
+        sm[L::LOSSJ + o * S + s] = c2 * (gmof_val(du, sigma2) + gmof_val(dv, sigma2));
+        if (with_grad) {
+            const float gu = c2 * gmof_grad(du, sigma2) * focal, gv = c2 * gmof_grad(dv, sigma2) * focal;
+            sm[L::OUTJ + (3 * o + 0) * S + s] = gu / Pz;
+            sm[L::OUTJ + (3 * o + 1) * S + s] = gv / Pz;
+            sm[L::OUTJ + (3 * o + 2) * S + s] = -(gu * px + gv * py) / Pz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// priors (smplify/prior.py:181-196 merged max-mixture; losses.py:19-24 angle prior; shape prior)
+// ------------------------------------------------------------------------------------------------
+template <int S>
+SB_HD void ph_prior_quadratic(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    // contrib[(g,i)][s] = (sum_j Psym_g[i][j] * bp[j] - (Psym_g mean_g)[i]) * (bp[i] - mean_g[i])
+    FOR_ITEMS(it, kGauss * kPriorDim) {
+        const int g = it / kPriorDim, i = it % kPriorDim;
+        float acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+        const float* P = M.gmm_prec + g * kPriorDim * kPriorDim + i;
+#pragma unroll 3
+        for (int j = 0; j < kPriorDim; ++j) {
+            const float c = P[j * kPriorDim];
+            const float* bp = sm + L::POSE + (3 + j) * S;
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[s] += c * bp[s];
+        }
+        const float pm = M.gmm_pmean[it], mu = M.gmm_means[it];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            sm[L::QT + it * S + s] = (acc[s] - pm) * (sm[L::POSE + (3 + i) * S + s] - mu);
+    }
+}
+
+template <int S>
+SB_HD void ph_prior_select(const ModelView& M, float* sm, float prior_w2, float angle_w2, float shape_w2,
+                           const int* angle_ids, const float* angle_signs) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kGauss * S) {
+        const int s = it % S, g = it / S;
+        float q = 0.f;
+        for (int i = 0; i < kPriorDim; ++i) q += sm[L::QT + (g * kPriorDim + i) * S + s];
+        sm[L::MISC + g * S + s] = 0.5f * q - M.gmm_lognll[g];
+    }
+    TILE_SYNC();
+    FOR_ITEMS(s, S) {
+        int best = 0;
+        float bv = sm[L::MISC + s];
+        for (int g = 1; g < kGauss; ++g) {
+            const float v = sm[L::MISC + g * S + s];
+            if (v < bv) { bv = v; best = g; }
+        }
+        sm[L::MISC + 8 * S + s] = (float)best;
+        sm[L::LOSSJ + 49 * S + s] = prior_w2 * bv;
+        float ang = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            const float e = expf(sm[L::POSE + (3 + angle_ids[a]) * S + s] * angle_signs[a]);
+            ang += e * e;
+        }
+        sm[L::LOSSJ + 50 * S + s] = angle_w2 * ang;
+        float sh = 0.f;
+        for (int l = 0; l < kBetas; ++l) sh += sm[L::BETA + l * S + s] * sm[L::BETA + l * S + s];
+        sm[L::LOSSJ + 51 * S + s] = shape_w2 * sh;
+    }
+    TILE_SYNC();
+    // gradient of the selected component: prior_w2 * Psym (bp - mean); plus the angle prior
+    FOR_ITEMS(it, kPriorDim * S) {
+        const int s = it % S, i = it / S;
+        const int g = (int)sm[L::MISC + 8 * S + s];
+        const float* P = M.gmm_prec + g * kPriorDim * kPriorDim + i;
+        float a = 0.f;
+        for (int j = 0; j < kPriorDim; ++j) a += P[j * kPriorDim] * sm[L::POSE + (3 + j) * S + s];
+        float gr = prior_w2 * (a - M.gmm_pmean[g * kPriorDim + i]);
+        for (int k = 0; k < 4; ++k)
+            if (angle_ids[k] == i) {
+                const float e = expf(sm[L::POSE + (3 + i) * S + s] * angle_signs[k]);
+                gr += angle_w2 * 2.0f * angle_signs[k] * e * e;
+            }
+        sm[L::GPR + i * S + s] = gr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward phases
+// ------------------------------------------------------------------------------------------------
+template <int S>
+SB_HD void source_grad(const ModelView& M, const float* sm, int src, int s, float* d) {
+    using L = TileLayout<S>;
+    d[0] = d[1] = d[2] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int o = M.inv_map[src][t];
+        if (o >= 0) {
+            d[0] += sm[L::OUTJ + (3 * o + 0) * S + s];
+            d[1] += sm[L::OUTJ + (3 * o + 1) * S + s];
+            d[2] += sm[L::OUTJ + (3 * o + 2) * S + s];
+        }
+    }
+}
+
+// dL/dA_j from the extra joints and the picked vertices, converted to dL/dG_j and dL/dJ_j.
+// extern_dA (may be null): additional dL/dA [24][12] rows per sample coming from the vertex path.
+template <int S>
+SB_HD void ph_joint_backward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kJoints * S) {
+        const int s = it % S, j = it / S;
+        float dAR[9], dAt[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dAR[e] = sm[L::DG + (j * 12 + (e / 3) * 4 + e % 3) * S + s];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dAt[r] = sm[L::DG + (j * 12 + r * 4 + 3) * S + s];
+        float G[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) G[r * 3 + c] = sm[L::GW + (j * 12 + r * 4 + c) * S + s];
+        for (int k = 0; k < kExtra; ++k) {
+            float dE[3];
+            source_grad<S>(M, sm, kJoints + kSelVerts + k, s, dE);
+            const int qb = (k * kJoints + j) * 3;
+            float* q0 = sm + L::QT + (qb + 0) * L::LDQ + s;
+            float* q1 = sm + L::QT + (qb + 1) * L::LDQ + s;
+            float* q2 = sm + L::QT + (qb + 2) * L::LDQ + s;
+            const float qx = *q0, qy = *q1, qz = *q2;
+            const float w = M.wkj[k * kJoints + j];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                dAR[r * 3 + 0] += dE[r] * qx; dAR[r * 3 + 1] += dE[r] * qy; dAR[r * 3 + 2] += dE[r] * qz;
+                dAt[r] += w * dE[r];
+            }
+            *q0 = G[0] * dE[0] + G[3] * dE[1] + G[6] * dE[2];
+            *q1 = G[1] * dE[0] + G[4] * dE[1] + G[7] * dE[2];
+            *q2 = G[2] * dE[0] + G[5] * dE[1] + G[8] * dE[2];
+        }
+        for (int p = 0; p < kPicks; ++p) {
+            float dV[3];
+            source_grad<S>(M, sm, kJoints + p, s, dV);
+            const float w = M.Wp[p * kJoints + j];
+            const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
+                        vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float wd = w * dV[r];
+                dAR[r * 3 + 0] += wd * vx; dAR[r * 3 + 1] += wd * vy; dAR[r * 3 + 2] += wd * vz;
+                dAt[r] += wd;
+            }
+        }
+        // A^R = G^R ; A^t = G^t - G^R J
+        const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s], Jz = sm[L::JR + (3 * j + 2) * S + s];
+        float dJt[3];
+        source_grad<S>(M, sm, j, s, dJt);           // the chain joint itself is G_j^t
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            sm[L::DG + (j * 12 + r * 4 + 0) * S + s] = dAR[r * 3 + 0] - dAt[r] * Jx;
+            sm[L::DG + (j * 12 + r * 4 + 1) * S + s] = dAR[r * 3 + 1] - dAt[r] * Jy;
+            sm[L::DG + (j * 12 + r * 4 + 2) * S + s] = dAR[r * 3 + 2] - dAt[r] * Jz;
+            sm[L::DG + (j * 12 + r * 4 + 3) * S + s] = dAt[r] + dJt[r];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            sm[L::DJ + (3 * j + c) * S + s] = -(G[0 + c] * dAt[0] + G[3 + c] * dAt[1] + G[6 + c] * dAt[2]);
+    }
+}
+
+// dL/d(v_posed of picked vertex) = (sum_j Wp[p][j] G_j^R)^T dL/dvert ; written over the pick rows of QT.
+template <int S>
+SB_HD void ph_pick_backward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, kPicks * S) {
+        const int s = it % S, p = it / S;
+        float dV[3];
+        source_grad<S>(M, sm, kJoints + p, s, dV);
+        float T[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) T[e] = 0.f;
+        for (int j = 0; j < kJoints; ++j) {
+            const float w = M.Wp[p * kJoints + j];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[r * 3 + c] += w * sm[L::GW + (j * 12 + r * 4 + c) * S + s];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            sm[L::QT + (kQPickBase + 3 * p + c) * L::LDQ + s] = T[0 + c] * dV[0] + T[3 + c] * dV[1] + T[6 + c] * dV[2];
+    }
+}
+
+// Reverse sweep of the kinematic chain.  Parents gather from their children level by level
+// (deterministic, no atomics); then every joint derives dL/dR_j (stored over RM) and the
+// rest-joint gradient DJ.
+template <int S>
+SB_HD void ph_chain_backward(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    for (int lev = M.num_levels - 2; lev >= 0; --lev) {
+        const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
+        FOR_ITEMS(it, cnt * S) {
+            const int s = it % S, p = M.level_order[first + it / S];
+            const int c0 = M.child_start[p], c1 = M.child_start[p + 1];
+            if (c0 == c1) continue;
+            float dGp[12], Gp[9], dJp[3];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) dGp[e] = sm[L::DG + (p * 12 + e) * S + s];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Gp[r * 3 + c] = sm[L::GW + (p * 12 + r * 4 + c) * S + s];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dJp[c] = sm[L::DJ + (3 * p + c) * S + s];
+            const float Jpx = sm[L::JR + (3 * p + 0) * S + s], Jpy = sm[L::JR + (3 * p + 1) * S + s], Jpz = sm[L::JR + (3 * p + 2) * S + s];
+            for (int ci = c0; ci < c1; ++ci) {
+                const int i = M.child_list[ci];
+                float dGi[12], Ri[9];
+#pragma unroll
+                for (int e = 0; e < 12; ++e) dGi[e] = sm[L::DG + (i * 12 + e) * S + s];
+#pragma unroll
+                for (int e = 0; e < 9; ++e) Ri[e] = sm[L::RM + (i * 9 + e) * S + s];
+                const float rel[3] = {sm[L::JR + (3 * i + 0) * S + s] - Jpx, sm[L::JR + (3 * i + 1) * S + s] - Jpy,
+                                      sm[L::JR + (3 * i + 2) * S + s] - Jpz};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        dGp[r * 4 + c] += dGi[r * 4 + 0] * Ri[c * 3 + 0] + dGi[r * 4 + 1] * Ri[c * 3 + 1] + dGi[r * 4 + 2] * Ri[c * 3 + 2]
+                                          + dGi[r * 4 + 3] * rel[c];
+                    dGp[r * 4 + 3] += dGi[r * 4 + 3];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)      // d(J_i - J_p) = G_p^R^T dG_i^t ; parent gets the minus sign
+                    dJp[c] -= Gp[0 + c] * dGi[3] + Gp[3 + c] * dGi[7] + Gp[6 + c] * dGi[11];
+            }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) sm[L::DG + (p * 12 + e) * S + s] = dGp[e];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sm[L::DJ + (3 * p + c) * S + s] = dJp[c];
+        }
+        TILE_SYNC();
+    }
+    FOR_ITEMS(it, kJoints * S) {
+        const int s = it % S, j = it / S, p = M.parents[j];
+        float dGi[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) dGi[e] = sm[L::DG + (j * 12 + e) * S + s];
+        if (p < 0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sm[L::RM + (j * 9 + r * 3 + c) * S + s] = dGi[r * 4 + c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sm[L::DJ + (3 * j + c) * S + s] += dGi[c * 4 + 3];
+        } else {
+            float Gp[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Gp[r * 3 + c] = sm[L::GW + (p * 12 + r * 4 + c) * S + s];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)   // dR_j = G_p^R^T dG_j^R
+                    sm[L::RM + (j * 9 + r * 3 + c) * S + s] = Gp[0 + r] * dGi[0 + c] + Gp[3 + r] * dGi[4 + c] + Gp[6 + r] * dGi[8 + c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                sm[L::DJ + (3 * j + c) * S + s] += Gp[0 + c] * dGi[3] + Gp[3 + c] * dGi[7] + Gp[6 + c] * dGi[11];
+        }
+    }
+}
+
+// dL/dR_j of body joints also receives the pose-feature gradient dx[11 + 9(j-1) + e].
+template <int S>
+SB_HD void rotation_grad(const float* sm, int j, int s, float* g) {
+    using L = TileLayout<S>;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+        g[e] = sm[L::RM + (j * 9 + e) * S + s];
+        if (j > 0) g[e] += sm[L::XT + (11 + (j - 1) * 9 + e) * S + s];
+    }
+}
+
+// dL/dbeta_l = dx[1+l] + sum_{j,c} JS[j][c][l] dJ[j][c]  (the prior term is added by the caller)
+template <int S>
+SB_HD float beta_grad(const ModelView& M, const float* sm, int l, int s) {
+    using L = TileLayout<S>;
+    float a = sm[L::XT + (1 + l) * S + s];
+    for (int jc = 0; jc < 72; ++jc) a += M.JS[jc * kBetas + l] * sm[L::DJ + jc * S + s];
+    return a;
+}
+
+template <int S>
+SB_HD void zero_rows(float* sm, int off, int rows) {
+    FOR_ITEMS(it, rows * S) sm[off + it] = 0.f;
+}
+
+}  // namespace smplb200

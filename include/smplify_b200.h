@@ -1,0 +1,143 @@
+/* C ABI of the B200-native SMPLify / SMPL library (libsmplify_b200.so).
+ *
+ * The reference (AnonymousSubmission43/Inbed_pose_estimation) has no FFI: its boundary for this
+ * path is a set of Python callables.  Each entry point below names the reference callable it
+ * replaces (paths into the reference tree); inbed_pose_estimation_b200/ binds them with ctypes
+ * underneath Python classes that keep the reference's signatures.
+ *
+ * Conventions
+ *  - every pointer marked "device" is a CUDA device pointer to contiguous row-major fp32 data;
+ *    the caller owns all input, output and workspace buffers; the library owns only the
+ *    immutable model-constant blob between model_create and model_destroy;
+ *  - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*), has no
+ *    hidden global state and is thread-compatible;
+ *  - return value 0 = success; anything else is an error whose text smplb200_last_error()
+ *    returns for the calling thread.  There is no CPU fallback: without a CUDA device
+ *    model_create fails.
+ */
+#ifndef SMPLIFY_B200_H_
+#define SMPLIFY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLB200_NUM_VERTS 6890
+#define SMPLB200_NUM_JOINTS 24
+#define SMPLB200_NUM_BETAS 10
+#define SMPLB200_NUM_POSE_FEATURES 207
+#define SMPLB200_NUM_OUT_JOINTS 49
+#define SMPLB200_NUM_GAUSSIANS 8
+#define SMPLB200_MAX_ITERS 256
+
+typedef struct smplb200_model smplb200_model;
+
+/* Host-side description of the model constants (all host pointers, copied during create).
+ * Mirrors what models/smpl.py:14-19 + smplx.SMPL.__init__ register as buffers and what
+ * smplify/prior.py:142-160 derives from gmm_08.pkl. */
+typedef struct {
+    const float* v_template;         /* [6890][3] */
+    const float* shapedirs;          /* [6890][3][10] */
+    const float* posedirs;           /* [6890][3][207]  (file layout, before smplx's reshape/transpose) */
+    const float* J_regressor;        /* [24][6890] */
+    const float* weights;            /* [6890][24] */
+    const float* J_regressor_extra;  /* [9][6890]   models/smpl.py:17-18 */
+    const int32_t* parents;          /* [24], root = -1 */
+    const int32_t* extra_vertex_ids; /* [21]  smplx VertexJointSelector */
+    const int32_t* joint_map;        /* [49] -> index into the 54 joints; models/smpl.py:16,19 */
+    const int32_t* ign_joints;       /* output joints zeroed for the body stage; smplify/smplify.py:28-29 */
+    int32_t num_ign_joints;          /* <= 8 */
+    const int32_t* cam_op_joints;    /* [4] smplify/losses.py:72-73 */
+    const int32_t* cam_gt_joints;    /* [4] smplify/losses.py:74-75 */
+    const int32_t* angle_prior_ids;  /* [4] body_pose entries; smplify/losses.py:24 */
+    const float* angle_prior_signs;  /* [4] */
+    const float* gmm_means;          /* [8][69]      may be NULL: SMPL only, no fitting */
+    const float* gmm_precisions;     /* [8][69][69]  prior.py:146-150 */
+    const float* gmm_nll_weights;    /* [8]          prior.py:153-160 */
+} smplb200_model_desc;
+
+int smplb200_version(void);
+const char* smplb200_last_error(void);
+
+/* Builds the constant blob on CUDA device `device` (folds the joint regressors in float64 on the
+ * host, uploads ~60 MB).  Replaces SMPL.__init__ (models/smpl.py:14-19) and
+ * MaxMixturePrior.__init__ (smplify/prior.py:102-174) as far as device state is concerned. */
+int smplb200_model_create(const smplb200_model_desc* desc, int device, smplb200_model** out);
+void smplb200_model_destroy(smplb200_model* model);
+
+/* Bytes of device workspace the calls below need for `batch` samples. */
+size_t smplb200_fit_workspace_bytes(int batch);
+size_t smplb200_smpl_workspace_bytes(int batch);
+
+/* SMPLify.__call__ (smplify/smplify.py:40-136): two-stage fit, num_iters Adam steps per stage.
+ * keypoints [B][49][3] is read AND its confidences at ign_joints are zeroed in place after the
+ * camera stage, exactly like the reference (:105).  vertices / loss_trace may be NULL.
+ * loss_trace [2*num_iters][B]: per-sample loss of every iteration (stage 1 then stage 2). */
+int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+                         const float* init_pose /*device [B][72]*/, const float* init_betas /*device [B][10]*/,
+                         const float* init_cam_t /*device [B][3]*/, const float* camera_center /*device [B][2]*/,
+                         float* keypoints_2d /*device [B][49][3], in/out*/,
+                         float* vertices /*device [B][6890][3] or NULL*/, float* joints /*device [B][49][3]*/,
+                         float* pose /*device [B][72]*/, float* betas /*device [B][10]*/, float* camera_translation /*device [B][3]*/,
+                         float* reprojection_loss /*device [B][49]*/, float* loss_trace /*device or NULL*/,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* SMPLify.get_fitting_loss (smplify/smplify.py:138-172): zeroes the ignored confidences in place
+ * (:156), one forward, per-joint reprojection loss [B][49]. */
+int smplb200_smplify_fitting_loss(const smplb200_model* model, int batch, float focal_length,
+                                  const float* pose, const float* betas, const float* cam_t, const float* camera_center,
+                                  float* keypoints_2d, float* reprojection_loss,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* SMPL.forward (models/smpl.py:21-33 -> smplx lbs).  rotmat_mode 0: pose is axis-angle [B][72]
+ * (global_orient ++ body_pose); 1: pose is [B][24][3][3] (pose2rot=False).  saved_vposed
+ * ([B][6890][3] or NULL) keeps v_posed for smplb200_smpl_backward. */
+int smplb200_smpl_forward(const smplb200_model* model, int batch, int rotmat_mode,
+                          const float* pose, const float* betas,
+                          float* vertices /*[B][6890][3] or NULL*/, float* joints /*[B][49][3]*/, float* saved_vposed,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient of the above w.r.t. pose (same layout as the input) and betas, given upstream
+ * gradients of vertices and/or joints (either may be NULL).  What torch autograd does through
+ * smplx in the reference (train/trainer.py:597-615 -> loss.backward()). */
+int smplb200_smpl_backward(const smplb200_model* model, int batch, int rotmat_mode,
+                           const float* pose, const float* betas, const float* saved_vposed,
+                           const float* grad_vertices, const float* grad_joints,
+                           float* grad_pose, float* grad_betas,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* utils/geometry.py:9-45 batch_rodrigues (quaternion form) and its gradient. */
+int smplb200_batch_rodrigues(int n, const float* theta /*[n][3]*/, float* rotmat /*[n][3][3]*/, void* stream);
+int smplb200_batch_rodrigues_backward(int n, const float* theta, const float* grad_rotmat, float* grad_theta, void* stream);
+
+/* utils/geometry.py:79-107 perspective_projection and its gradient.  focal_length is a device
+ * pointer to 1 value (focal_per_batch = 0) or to [B] values (focal_per_batch = 1). */
+int smplb200_perspective_projection(int batch, int num_points, const float* points, const float* rotation,
+                                    const float* translation, const float* focal_length, int focal_per_batch,
+                                    const float* camera_center, float* projected /*[B][N][2]*/, void* stream);
+int smplb200_perspective_projection_backward(int batch, int num_points, const float* points, const float* rotation,
+                                             const float* translation, const float* focal_length, int focal_per_batch,
+                                             const float* grad_projected, float* grad_points, float* grad_rotation,
+                                             float* grad_translation, void* stream);
+
+/* Host-buffer convenience wrapper of smplb200_smplify_fit: all pointers are HOST pointers
+ * (pinned for best throughput); copies inputs to the device, runs the fit, copies the results
+ * back and synchronises.  vertices may be NULL (they are then left on the device and not
+ * copied).  This is the call timed as "e2e" by bench.py. */
+int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+                              const float* init_pose, const float* init_betas, const float* init_cam_t,
+                              const float* camera_center, float* keypoints_2d,
+                              float* vertices, float* joints, float* pose, float* betas, float* camera_translation,
+                              float* reprojection_loss);
+
+/* Number of this library's kernel launches issued by the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+long long smplb200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPLIFY_B200_H_ */

@@ -1,0 +1,120 @@
+"""Host emulation of the CUDA tile code (tests/emu) against the oracle - CPU only.
+
+This checks the arithmetic the GPU kernels execute (the phases are the same source,
+compiled for the host): folded joint model, hand-derived backward pass, priors, Adam,
+two-stage control flow.  The GPU parity tests proper are in test_gpu_*.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from inbed_pose_estimation_b200 import constants as C, synthetic
+from emu import emu as emu_mod
+
+pytestmark = pytest.mark.skipif(not emu_mod.available(), reason='nvcc needed to build the emulation library')
+
+
+@pytest.fixture(scope='module')
+def emu():
+    return emu_mod.Emu(seed=0)
+
+
+def test_forward_joints_and_transforms(emu, oracle_fp32):
+    g = golden('smpl_forward.npz')
+    joints, A, x = emu.pose_forward(g['pose'], g['betas'])
+    np.testing.assert_allclose(joints, g['joints'], atol=2e-6)
+    joints_r, A_r, _ = emu.pose_forward(g['rotmats'].reshape(4, 216), g['betas'], rotmat_mode=True)
+    np.testing.assert_allclose(joints_r, g['joints_rotmat'], atol=2e-6)
+    # A and x reproduce the oracle's vertices through plain numpy skinning
+    arrays = emu_mod.model_arrays(0)
+    basis = emu.array('basis').reshape(224, -1)[:218, :20670]
+    vp = (x[:, :218].astype(np.float64) @ basis.astype(np.float64)).reshape(4, 6890, 3)
+    T = np.einsum('vj,bje->bve', arrays['weights'].astype(np.float64), A.reshape(4, 24, 12).astype(np.float64)).reshape(4, 6890, 3, 4)
+    verts = np.einsum('bvrc,bvc->bvr', T[..., :3], vp) + T[..., 3]
+    np.testing.assert_allclose(verts[:, ::8], g['vertices_sub'], atol=3e-6)
+
+
+def test_backward_joints_matches_autograd(emu, oracle_fp32):
+    rs = np.random.RandomState(5)
+    inp = synthetic.make_fit_inputs(6, seed=11)
+    dj = rs.randn(6, 49, 3).astype(np.float32)
+    pose = torch.tensor(inp['pose'], dtype=torch.float64, requires_grad=True)
+    betas = torch.tensor(inp['betas'], dtype=torch.float64, requires_grad=True)
+    smpl64 = _oracle64().smpl
+    out = smpl64(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
+    (out.joints * torch.tensor(dj, dtype=torch.float64)).sum().backward()
+    d_pose, d_betas = emu.pose_backward(inp['pose'], inp['betas'], d_joints=dj)
+    np.testing.assert_allclose(d_pose, pose.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(d_betas, betas.grad.numpy(), rtol=2e-4, atol=2e-5)
+    # rotation-matrix mode
+    from oracle import port
+    R = port.exp_map_rodrigues(torch.tensor(inp['pose'], dtype=torch.float64).reshape(-1, 3)).view(6, 24, 3, 3)
+    R = R.clone().requires_grad_(True)
+    b2 = torch.tensor(inp['betas'], dtype=torch.float64, requires_grad=True)
+    out = smpl64(global_orient=R[:, :1], body_pose=R[:, 1:], betas=b2, pose2rot=False)
+    (out.joints * torch.tensor(dj, dtype=torch.float64)).sum().backward()
+    d_R, d_b = emu.pose_backward(R.detach().numpy().reshape(6, 216).astype(np.float32), inp['betas'], d_joints=dj, rotmat_mode=True)
+    np.testing.assert_allclose(d_R, R.grad.numpy().reshape(6, 216), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(d_b, b2.grad.numpy(), rtol=2e-4, atol=2e-5)
+
+
+_O64 = []
+
+
+def _oracle64():
+    if not _O64:
+        from oracle import port
+        _O64.append(port.build_oracle(seed=0, dtype=torch.float64))
+    return _O64[0]
+
+
+def test_backward_vertex_path_matches_autograd(emu):
+    """dL/dA and dL/dx fed in from the vertex kernels reach pose and betas correctly."""
+    rs = np.random.RandomState(6)
+    inp = synthetic.make_fit_inputs(4, seed=12)
+    smpl64 = _oracle64().smpl
+    pose = torch.tensor(inp['pose'], dtype=torch.float64, requires_grad=True)
+    betas = torch.tensor(inp['betas'], dtype=torch.float64, requires_grad=True)
+    out = smpl64(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
+    gv = rs.randn(4, 6890, 3)
+    (out.vertices * torch.tensor(gv)).sum().backward()
+    # numpy restatement of what lbs_vertex_backward_kernel produces
+    arrays = emu_mod.model_arrays(0)
+    _, A, x = emu.pose_forward(inp['pose'], inp['betas'])
+    basis = emu.array('basis').reshape(224, -1)[:, :20670].astype(np.float64)
+    W = arrays['weights'].astype(np.float64)
+    vp = (x.astype(np.float64) @ basis).reshape(4, 6890, 3)
+    T = np.einsum('vj,bje->bve', W, A.reshape(4, 24, 12).astype(np.float64)).reshape(4, 6890, 3, 4)
+    dvp = np.einsum('bvrc,bvr->bvc', T[..., :3], gv)
+    dT = np.concatenate([gv[..., None] * vp[:, :, None, :], gv[..., None]], axis=-1)      # [B,V,3,4]
+    dA = np.einsum('vj,bve->bje', W, dT.reshape(4, 6890, 12)).astype(np.float32)
+    dx = (dvp.reshape(4, -1) @ basis.T).astype(np.float32)
+    d_pose, d_betas = emu.pose_backward(inp['pose'], inp['betas'], dA=dA, dx=dx)
+    np.testing.assert_allclose(d_pose, pose.grad.numpy(), rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(d_betas, betas.grad.numpy(), rtol=3e-4, atol=3e-4)
+
+
+def test_fitting_loss_and_side_effect(emu):
+    g = golden('smplify_default.npz')
+    inp = {k: g[k] for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')}
+    out = emu.fit(inp, loss_only=True)
+    np.testing.assert_allclose(out['reproj'], g['init_fitting_loss'], rtol=2e-5, atol=1e-3)
+    assert np.array_equal(out['keypoints'], g['keypoints_after_loss'])
+
+
+@pytest.mark.parametrize('variant', ['default', 'trainer', 'slp'])
+def test_fit_matches_reference_run(emu, variant):
+    """100 + 100 iterations against the vectors the reference's own files produced."""
+    g = golden('smplify_%s.npz' % variant)
+    inp = {k: g[k] for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')}
+    out = emu.fit(inp, num_iters=100)
+    sums = out['trace'].astype(np.float64).sum(axis=1)
+    np.testing.assert_allclose(sums, g['loss_trace'], rtol=1e-5)
+    np.testing.assert_allclose(out['pose'], g['out_pose'], atol=1e-4)
+    np.testing.assert_allclose(out['betas'], g['out_betas'], atol=1e-4)
+    np.testing.assert_allclose(out['cam_t'], g['out_cam_t'], atol=1e-4)
+    np.testing.assert_allclose(out['joints'], g['out_joints'], atol=1e-4)
+    np.testing.assert_allclose(out['reproj'], g['out_reproj'], rtol=1e-4, atol=1e-2)
+    assert np.all(out['keypoints'][:, C.SMPLIFY_IGNORED_JOINTS, 2] == 0)
+    keep = [j for j in range(49) if j not in C.SMPLIFY_IGNORED_JOINTS]
+    assert np.array_equal(out['keypoints'][:, keep], g['keypoints'][:, keep])
