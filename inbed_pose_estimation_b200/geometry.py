@@ -1,0 +1,95 @@
+"""Geometry ops of the hot path with the reference's signatures (utils/geometry.py), CUDA-backed.
+
+batch_rodrigues        - utils/geometry.py:9-23 (+ quat_to_rotmat :25-45)
+perspective_projection - utils/geometry.py:79-107
+Both are differentiable (hand-written backward kernels) and CUDA only.
+"""
+import torch
+
+from . import _native
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _require_cuda(t, name):
+    if t.device.type != 'cuda':
+        raise RuntimeError('%s runs on CUDA (sm_100a) only; got a tensor on %s - there is no CPU fallback' % (name, t.device))
+
+
+class _Rodrigues(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta):
+        th = theta.detach().contiguous().float()
+        out = torch.empty((th.shape[0], 3, 3), device=th.device, dtype=torch.float32)
+        with torch.cuda.device(th.device):
+            _native.check(_native.lib().smplb200_batch_rodrigues(th.shape[0], _native.ptr(th), _native.ptr(out), _stream(th.device)))
+        ctx.save_for_backward(th)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (th,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        d = torch.empty_like(th)
+        with torch.cuda.device(th.device):
+            _native.check(_native.lib().smplb200_batch_rodrigues_backward(th.shape[0], _native.ptr(th), _native.ptr(g), _native.ptr(d),
+                                                                          _stream(th.device)))
+        return d
+
+
+def batch_rodrigues(theta):
+    """Axis-angle [N,3] -> rotation matrices [N,3,3] through the normalised half-angle quaternion."""
+    _require_cuda(theta, 'batch_rodrigues')
+    if theta.dim() != 2 or theta.shape[1] != 3:
+        raise ValueError('theta must be [N, 3]')
+    return _Rodrigues.apply(theta)
+
+
+class _Projection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, rotation, translation, focal, center):
+        B, N = points.shape[0], points.shape[1]
+        dev = points.device
+        p = points.detach().contiguous().float()
+        r = rotation.detach().expand(B, 3, 3).contiguous().float()
+        t = translation.detach().contiguous().float()
+        c = center.detach().contiguous().float()
+        per_batch = int(focal.numel() > 1)
+        out = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().smplb200_perspective_projection(
+                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), per_batch, _native.ptr(c),
+                _native.ptr(out), _stream(dev)))
+        ctx.save_for_backward(p, r, t, focal)
+        ctx.per_batch = per_batch
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        p, r, t, focal = ctx.saved_tensors
+        B, N = p.shape[0], p.shape[1]
+        g = g.contiguous().float()
+        gp, gr, gt = torch.empty_like(p), torch.empty_like(r), torch.empty_like(t)
+        with torch.cuda.device(p.device):
+            _native.check(_native.lib().smplb200_perspective_projection_backward(
+                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), ctx.per_batch, _native.ptr(g),
+                _native.ptr(gp), _native.ptr(gr), _native.ptr(gt), _stream(p.device)))
+        return gp, gr, gt, None, None
+
+
+def perspective_projection(points, rotation, translation, focal_length, camera_center, out_3d=False):
+    """points [B,N,3], rotation [B,3,3], translation [B,3], focal_length scalar or [B],
+    camera_center [B,2] -> [B,N,2].  (The reference's out_3d=True variant is off the hot path.)"""
+    if out_3d:
+        raise NotImplementedError('out_3d=True is not part of the hot path')
+    _require_cuda(points, 'perspective_projection')
+    B = points.shape[0]
+    if torch.is_tensor(focal_length):
+        focal = focal_length.detach().to(points.device, torch.float32).reshape(-1).contiguous()
+        if focal.numel() not in (1, B):
+            raise ValueError('focal_length must be a scalar or have one entry per batch element')
+    else:
+        focal = torch.full((1,), float(focal_length), device=points.device, dtype=torch.float32)
+    return _Projection.apply(points, rotation, translation, focal, camera_center)

@@ -56,6 +56,18 @@ class MaxMixturePrior(torch.nn.Module):
             sys.exit(-1)
         with open(full_gmm_fn, 'rb') as f:
             gmm = pickle.load(f, encoding='latin1')
+        self._init_from_gmm(gmm)
+
+    @classmethod
+    def from_gmm(cls, gmm, num_gaussians=8):
+        """Build the prior from an in-memory gmm dict (tests and benchmarks: no file on disk)."""
+        self = cls.__new__(cls)
+        torch.nn.Module.__init__(self)
+        self.num_gaussians, self.epsilon, self.use_merged = num_gaussians, 1e-16, True
+        self._init_from_gmm(gmm)
+        return self
+
+    def _init_from_gmm(self, gmm):
         try:
             consts = gmm_constants(gmm)
         except TypeError as e:

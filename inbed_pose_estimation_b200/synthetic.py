@@ -95,3 +95,25 @@ def make_fit_inputs(batch, seed=0, variant='default'):
     elif variant != 'default':
         raise ValueError('unknown variant %r' % (variant,))
     return {'pose': pose, 'betas': betas, 'cam_t': cam_t, 'center': center, 'keypoints': kp}
+
+
+def model_arrays(seed=0):
+    """The synthetic model as the float32 arrays SMPL(model_arrays=...) takes."""
+    m = make_smpl_model(seed)
+    arrays = {k: np.asarray(m[k], dtype=np.float32) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights')}
+    parents = np.asarray(m['kintree_table'][0]).astype(np.int64)
+    parents[0] = -1
+    arrays['parents'] = parents
+    arrays['faces'] = np.asarray(m['f']).astype(np.int64)
+    return arrays
+
+
+def build_smplify(device='cuda', num_iters=100, seed=0, step_size=1e-2, focal_length=5000):
+    """SMPLify on the synthetic model, no files needed."""
+    from .prior import MaxMixturePrior
+    from .smpl import SMPL
+    from .smplify import SMPLify
+    smpl = SMPL(model_arrays=model_arrays(seed), j_regressor_extra=make_extra_regressor(seed + 1))
+    prior = MaxMixturePrior.from_gmm(make_gmm(seed + 2))
+    return SMPLify(step_size=step_size, num_iters=num_iters, focal_length=focal_length, device=device,
+                   smpl=smpl, pose_prior=prior)

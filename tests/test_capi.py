@@ -1,0 +1,55 @@
+"""The C-ABI library builds, loads and exports every symbol include/smplify_b200.h declares.
+No compute calls (CPU-only box)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from inbed_pose_estimation_b200 import _native
+
+
+def _declared():
+    text = open(os.path.join(ROOT, 'include', 'smplify_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(smplb200_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    path = _native.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), 'missing export ' + n
+    assert sorted(_native.EXPORTED_SYMBOLS) == names
+    assert _native.lib().smplb200_version() == 100
+
+
+def test_model_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from inbed_pose_estimation_b200 import synthetic
+    arrays = synthetic.model_arrays(0)
+    arrays['J_regressor_extra'] = synthetic.make_extra_regressor(1)
+    with pytest.raises(RuntimeError, match='no CUDA device|CPU fallback'):
+        _native.NativeModel(arrays, None, 0)
+
+
+def test_workspace_queries():
+    lib = _native.lib()
+    assert lib.smplb200_fit_workspace_bytes(0) >= 0
+    assert lib.smplb200_fit_workspace_bytes(4096) >= 4096 * 512 * 4
+    assert lib.smplb200_smpl_workspace_bytes(32) >= 32 * 512 * 4 * 9
+
+
+def test_host_side_validation():
+    """Python wrappers reject CPU tensors and bad shapes before reaching the device."""
+    import torch
+    from inbed_pose_estimation_b200 import geometry
+    with pytest.raises(RuntimeError, match='CUDA'):
+        geometry.batch_rodrigues(torch.zeros(3, 3))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        geometry.perspective_projection(torch.zeros(1, 2, 3), torch.eye(3)[None], torch.zeros(1, 3), 5000., torch.zeros(1, 2))

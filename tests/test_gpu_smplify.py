@@ -1,0 +1,110 @@
+"""GPU parity of the fused SMPLify fit (through the C ABI) against the oracle and the
+reference-generated golden vectors.  Tolerances are BASELINE.json's: fitted parameters,
+joints and vertices within 1e-4 absolute, per-iteration losses within 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from inbed_pose_estimation_b200 import constants as C, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def fitter():
+    return synthetic.build_smplify('cuda', num_iters=100, seed=0)
+
+
+def _cuda(inp):
+    return [torch.from_numpy(inp[k].copy()).cuda() for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')]
+
+
+@pytest.mark.parametrize('variant', ['default', 'trainer', 'slp'])
+def test_fit_matches_reference_golden(fitter, variant):
+    g = golden('smplify_%s.npz' % variant)
+    args = _cuda({k: g[k] for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')})
+    v, j, pose, betas, cam, reproj = fitter(*args, return_loss_trace=True)
+    trace = fitter.last_loss_trace.double().sum(dim=1).cpu().numpy()
+    np.testing.assert_allclose(trace, g['loss_trace'], rtol=1e-5)
+    np.testing.assert_allclose(pose.cpu().numpy(), g['out_pose'], atol=1e-4)
+    np.testing.assert_allclose(betas.cpu().numpy(), g['out_betas'], atol=1e-4)
+    np.testing.assert_allclose(cam.cpu().numpy(), g['out_cam_t'], atol=1e-4)
+    np.testing.assert_allclose(j.cpu().numpy(), g['out_joints'], atol=1e-4)
+    np.testing.assert_allclose(v.cpu().numpy()[:, ::8], g['out_vertices_sub'], atol=1e-4)
+    np.testing.assert_allclose(reproj.cpu().numpy(), g['out_reproj'], rtol=1e-4, atol=1e-2)
+    kp = args[4].cpu().numpy()
+    assert np.all(kp[:, C.SMPLIFY_IGNORED_JOINTS, 2] == 0)           # in-place side effect (smplify.py:105)
+    keep = [k for k in range(49) if k not in C.SMPLIFY_IGNORED_JOINTS]
+    assert np.array_equal(kp[:, keep], g['keypoints'][:, keep])
+    for t in (v, j, pose, betas, cam, reproj):
+        assert not t.requires_grad
+
+
+def test_fit_matches_oracle_batch32(fitter, oracle_fp32):
+    """BASELINE config 2 (B=32, 100+100 iterations), per-sample losses of every iteration."""
+    inp = synthetic.make_fit_inputs(32, seed=21)
+    trace_o = []
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    vo, jo, po, bo, co, ro = oracle_fp32(*[torch.from_numpy(inp[k].copy()) for k in
+                                           ('pose', 'betas', 'cam_t', 'center', 'keypoints')], trace=trace_o)
+    v, j, pose, betas, cam, reproj = fitter(*_cuda(inp), return_loss_trace=True)
+    tr = fitter.last_loss_trace.cpu().numpy()
+    tr_o = torch.stack(trace_o).numpy()
+    np.testing.assert_allclose(tr.astype(np.float64).sum(1), tr_o.astype(np.float64).sum(1), rtol=1e-5)
+    np.testing.assert_allclose(tr, tr_o, rtol=5e-5)                  # per sample
+    np.testing.assert_allclose(pose.cpu().numpy(), po.numpy(), atol=1e-4)
+    np.testing.assert_allclose(betas.cpu().numpy(), bo.numpy(), atol=1e-4)
+    np.testing.assert_allclose(cam.cpu().numpy(), co.detach().numpy(), atol=1e-4)
+    np.testing.assert_allclose(j.cpu().numpy(), jo.numpy(), atol=1e-4)
+    np.testing.assert_allclose(v.cpu().numpy(), vo.numpy(), atol=1e-4)
+
+
+def test_fitting_loss_matches_golden(fitter):
+    g = golden('smplify_default.npz')
+    args = _cuda({k: g[k] for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')})
+    loss = fitter.get_fitting_loss(*args)
+    np.testing.assert_allclose(loss.cpu().numpy(), g['init_fitting_loss'], rtol=2e-5, atol=1e-3)
+    assert np.array_equal(args[4].cpu().numpy(), g['keypoints_after_loss'])
+
+
+def test_non_contiguous_keypoints_side_effect(fitter):
+    """The confidence zeroing must reach the caller's tensor even through a strided view."""
+    inp = synthetic.make_fit_inputs(5, seed=3)
+    big = torch.zeros(5, 49, 4, device='cuda')
+    big[:, :, :3] = torch.from_numpy(inp['keypoints']).cuda()
+    view = big[:, :, :3]
+    fitter.get_fitting_loss(*(_cuda(inp)[:4] + [view]))
+    assert torch.all(view[:, C.SMPLIFY_IGNORED_JOINTS, 2] == 0)
+    assert torch.all(view[:, 0, 2] == 1)
+
+
+def test_batch_4096_properties(fitter):
+    """Full-size batch: every sample's fit is independent of its neighbours (sharding premise),
+    ragged tail tiles work, the loss decreases, repeated runs are bit-identical."""
+    B = 4096 + 7
+    inp = synthetic.make_fit_inputs(B, seed=5)
+    out = fitter(*_cuda(inp), return_loss_trace=True)
+    trace = fitter.last_loss_trace.cpu().numpy()
+    assert np.all(np.isfinite(trace)) and all(torch.isfinite(t).all() for t in out)
+    assert trace[199].sum() < trace[100].sum() and trace[99].sum() < trace[0].sum()
+    out2 = fitter(*_cuda(inp))
+    for a, b in zip(out, out2):
+        assert torch.equal(a, b)                                      # deterministic
+    sub = {k: v[1000:1050] for k, v in inp.items()}
+    out_sub = fitter(*_cuda(sub))
+    for a, b in zip(out, out_sub):
+        np.testing.assert_allclose(a[1000:1050].cpu().numpy(), b.cpu().numpy(), atol=2e-5)
+    ro = fitter.get_fitting_loss(out[2], out[3], out[4], torch.from_numpy(inp['center']).cuda(),
+                                 torch.from_numpy(inp['keypoints'].copy()).cuda())
+    np.testing.assert_allclose(ro.cpu().numpy(), out[5].cpu().numpy(), rtol=1e-5, atol=1e-3)
+
+
+def test_empty_batch_and_errors(fitter):
+    z = lambda *s: torch.zeros(*s, device='cuda')
+    out = fitter(z(0, 72), z(0, 10), z(0, 3), z(0, 2), z(0, 49, 3))
+    assert out[0].shape == (0, 6890, 3) and out[5].shape == (0, 49)
+    with pytest.raises(ValueError):
+        fitter(z(2, 72), z(2, 10), z(2, 3), z(2, 2), z(2, 48, 3))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        fitter(torch.zeros(2, 72), z(2, 10), z(2, 3), z(2, 2), z(2, 49, 3))
