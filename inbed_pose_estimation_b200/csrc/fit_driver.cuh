@@ -36,16 +36,39 @@ constexpr float kAnglePriorW2 = (float)(15.2 * 15.2); // angle_prior_weight ** 2
 constexpr float kShapePriorW2 = 25.f;                 // shape_prior_weight ** 2
 constexpr float kDepthW2 = 100.f * 100.f;             // depth_loss_weight ** 2 (losses.py:61)
 
+// Stage the small constants in shared memory (device) or just point at them (host emulation).
+// The caller must place a barrier before the first use.
+template <int S>
+SB_HD SmallConsts stage_small_consts(const ModelView& M, float* sm) {
+    SmallConsts C;
+#if defined(__CUDA_ARCH__)
+    float* b = sm + TileLayout<S>::CONSTS;
+    float* JS = b; float* J0 = JS + 720; float* wkj = J0 + 72; float* Wp = wkj + 216;
+    float* mu = Wp + 264; float* pmean = mu + 576; float* lognll = pmean + 576;
+    FOR_ITEMS(i, 720) JS[i] = M.JS[i];
+    FOR_ITEMS(i, 72) J0[i] = M.J0[i];
+    FOR_ITEMS(i, 216) wkj[i] = M.wkj[i];
+    FOR_ITEMS(i, 264) Wp[i] = M.Wp[i];
+    FOR_ITEMS(i, 576) { mu[i] = M.gmm_means[i]; pmean[i] = M.gmm_pmean[i]; }
+    FOR_ITEMS(i, 8) lognll[i] = M.gmm_lognll[i];
+    C.JS = JS; C.J0 = J0; C.wkj = wkj; C.Wp = Wp; C.mu = mu; C.pmean = pmean; C.lognll = lognll;
+#else
+    (void)sm;
+    C.JS = M.JS; C.J0 = M.J0; C.wkj = M.wkj; C.Wp = M.Wp; C.mu = M.gmm_means; C.pmean = M.gmm_pmean; C.lognll = M.gmm_lognll;
+#endif
+    return C;
+}
+
 // forward through the folded joint model for the tile's current parameters
 template <int S>
-SB_HD void tile_forward(const ModelView& M, float* sm, bool from_axis_angle, bool root_identity) {
+SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, bool from_axis_angle, bool root_identity) {
     ph_pose_features<S>(sm, from_axis_angle, root_identity);
-    ph_rest_joints<S>(M, sm);
+    ph_rest_joints<S>(C, sm);
     TILE_SYNC();
     ph_chain_forward<S>(M, sm);           // ends with a barrier
     ph_fold_gemm_forward<S>(M, sm);
     TILE_SYNC();
-    ph_output_joints<S>(M, sm);
+    ph_output_joints<S>(M, C, sm);
     TILE_SYNC();
 }
 
@@ -55,7 +78,7 @@ SB_HD void tile_forward(const ModelView& M, float* sm, bool from_axis_angle, boo
 template <int S>
 SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int tile, float* sm) {
     using L = TileLayout<S>;
-    const AdamScalars* adam_tab = reinterpret_cast<const AdamScalars*>(sm + L::TOTAL);
+    const AdamScalars* adam_tab = reinterpret_cast<const AdamScalars*>(sm + L::ADAMTAB);
     FOR_ITEMS(s, S) {
         const int b = tile * S + s;
         float th[3], t[3], mm[6], vv[6];
@@ -138,7 +161,8 @@ template <int S>
 SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm) {
     using L = TileLayout<S>;
     // per-iteration Adam scalars, computed in float64 like torch does on the host
-    AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::TOTAL);
+    AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::ADAMTAB);
+    const SmallConsts C = stage_small_consts<S>(M, sm);
     FOR_ITEMS(t, P.num_iters) {
         const double bc1 = 1.0 - pow(P.beta1, (double)(t + 1));
         const double bc2 = 1.0 - pow(P.beta2, (double)(t + 1));
@@ -171,7 +195,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
 
     if (P.num_iters > 0) {
         // ---- stage 1: global orientation + camera translation --------------------------------
-        tile_forward<S>(M, sm, true, /*root_identity=*/true);
+        tile_forward<S>(M, C, sm, true, /*root_identity=*/true);
         stage1_camera<S>(M, P, tile, sm);
         TILE_SYNC();
         tile_zero_ignored_conf<S>(M, P, tile, sm);
@@ -180,11 +204,11 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
 
         // ---- stage 2: body pose, betas, global orientation (body_fitting_loss) ----------------
         for (int it = 0; it < P.num_iters; ++it) {
-            ph_prior_quadratic<S>(M, sm);
+            ph_prior_quadratic<S>(M, C, sm);
             TILE_SYNC();
-            ph_prior_select<S>(M, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, M.angle_ids, M.angle_signs);
+            ph_prior_select<S>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
             TILE_SYNC();
-            tile_forward<S>(M, sm, true, false);
+            tile_forward<S>(M, C, sm, true, false);
             ph_reprojection<S>(sm, P.focal, kSigma2, true);
             zero_rows<S>(sm, L::DG, 288);
             TILE_SYNC();
@@ -197,9 +221,9 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
                     if (b < P.batch) P.loss_trace[(size_t)(P.num_iters + it) * P.batch + b] = a;
                 }
             }
-            ph_joint_backward<S>(M, sm);
+            ph_joint_backward<S>(M, C, sm);
             TILE_SYNC();
-            ph_pick_backward<S>(M, sm);
+            ph_pick_backward<S>(M, C, sm);
             TILE_SYNC();
             ph_fold_gemm_backward<S>(M, sm);
             TILE_SYNC();
@@ -223,7 +247,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
             FOR_ITEMS(itb, kBetas * S) {
                 const int s = itb % S, l = itb / S;
                 const float beta = sm[L::BETA + l * S + s];
-                const float g = beta_grad<S>(M, sm, l, s) + 2.f * kShapePriorW2 * beta;
+                const float g = beta_grad<S>(C, sm, l, s) + 2.f * kShapePriorW2 * beta;
                 sm[L::BETA + l * S + s] = adam_update(beta, g, sm[L::ADM + (72 + l) * S + s], sm[L::ADV + (72 + l) * S + s],
                                                       P.adam_c, sc);
             }
@@ -232,7 +256,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
     }
 
     // ---- final forward: joints, per-joint reprojection loss, A and x for the vertex kernel --------
-    tile_forward<S>(M, sm, true, false);
+    tile_forward<S>(M, C, sm, true, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
@@ -312,8 +336,9 @@ SB_HD void pose_load(const PoseParams& P, int tile, float* sm) {
 template <int S>
 SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
     using L = TileLayout<S>;
+    const SmallConsts C = stage_small_consts<S>(M, sm);
     pose_load<S>(P, tile, sm);
-    tile_forward<S>(M, sm, !P.rotmat_mode, false);
+    tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
@@ -333,8 +358,9 @@ SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, 
 template <int S>
 SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
     using L = TileLayout<S>;
+    const SmallConsts C = stage_small_consts<S>(M, sm);
     pose_load<S>(P, tile, sm);
-    tile_forward<S>(M, sm, !P.rotmat_mode, false);
+    tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = tile * S + s;
         sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
@@ -347,9 +373,9 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
         sm[L::DG + k * S + s] = a;
     }
     TILE_SYNC();
-    ph_joint_backward<S>(M, sm);
+    ph_joint_backward<S>(M, C, sm);
     TILE_SYNC();
-    ph_pick_backward<S>(M, sm);
+    ph_pick_backward<S>(M, C, sm);
     TILE_SYNC();
     ph_fold_gemm_backward<S>(M, sm);
     TILE_SYNC();
@@ -384,7 +410,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
     }
     FOR_ITEMS(it, kBetas * S) {
         const int s = it % S, l = it / S, b = tile * S + s;
-        const float g = beta_grad<S>(M, sm, l, s);
+        const float g = beta_grad<S>(C, sm, l, s);
         if (b < P.batch) P.d_betas[(size_t)b * kBetas + l] = g;
     }
 }

@@ -28,6 +28,28 @@ namespace smplb200 {
 #define TILE_SYNC() ((void)0)
 #endif
 #define FOR_ITEMS(it, n) for (int it = TILE_TID; it < (n); it += TILE_NT)
+#define TILE_SYNC_NONE() ((void)0)
+
+// Small per-model constants every iteration touches; the kernels stage them in shared memory once
+// (global / L2 latency would otherwise be exposed in the short per-sample phases).
+struct SmallConsts {
+    const float* JS;      // [72][10]
+    const float* J0;      // [72]
+    const float* wkj;     // [9][24]
+    const float* Wp;      // [11][24]
+    const float* mu;      // [8][72]  gmm means (padded)
+    const float* pmean;   // [8][72]  Psym . mean (padded)
+    const float* lognll;  // [8]
+};
+constexpr int kSmallConstFloats = 720 + 72 + 216 + 264 + 576 + 576 + 8;   // 2432
+
+SB_HD float2 ld_const2(const float2* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 template <int S>
 struct TileLayout {
@@ -52,7 +74,11 @@ struct TileLayout {
     static constexpr int ADV = ADM + 82 * S;        // [82][S]
     static constexpr int MISC = ADV + 82 * S;       // [16][S]
     static constexpr int TOTAL = MISC + 16 * S;
-    static_assert(kGauss * kPriorDim * S <= kQPad * LDQ, "prior scratch must fit in the QT region");
+    static constexpr int ADAMTAB = TOTAL;                       // [kMaxIters] AdamScalars
+    static constexpr int CONSTS = ADAMTAB + 2 * kMaxIters;      // SmallConsts arrays
+    static constexpr int SMEM_FLOATS = CONSTS + kSmallConstFloats;
+    static_assert(kGauss * kPriorPad * S <= kQPad * LDQ, "prior scratch must fit in the QT region");
+    static_assert(2 * kXPad * S <= kQPad * LDQ, "backward GEMM partials must fit in the QT region");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -172,13 +198,13 @@ SB_HD void ph_pose_features(float* sm, bool from_axis_angle, bool root_identity)
 
 // J = J0 + JS.beta  (== J_regressor.(v_template + shapedirs.beta), folded in float64 at model creation)
 template <int S>
-SB_HD void ph_rest_joints(const ModelView& M, float* sm) {
+SB_HD void ph_rest_joints(const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, 72 * S) {
         const int s = it % S, jc = it / S;
-        float a = M.J0[jc];
+        float a = C.J0[jc];
 #pragma unroll
-        for (int l = 0; l < kBetas; ++l) a += M.JS[jc * kBetas + l] * sm[L::BETA + l * S + s];
+        for (int l = 0; l < kBetas; ++l) a += C.JS[jc * kBetas + l] * sm[L::BETA + l * S + s];
         sm[L::JR + jc * S + s] = a;
     }
 }
@@ -228,64 +254,135 @@ SB_HD void ph_chain_forward(const ModelView& M, float* sm) {
 }
 
 // QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
+// One thread owns two adjacent columns for all S samples (2S accumulators); the basis rows are
+// streamed from L2 with U rows in flight per thread, x is broadcast from shared memory.
 template <int S>
 SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
-    FOR_ITEMS(n, kQ) {
-        float acc[S];
+    constexpr int U = 8, NP = kQPad / 2;
+    static_assert(kXPad % U == 0, "k padding");
+    FOR_ITEMS(t, NP) {
+        float a0[S], a1[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) acc[s] = 0.f;
-        const float* cf = M.Cf + n;
-#pragma unroll 4
-        for (int m = 0; m < kX; ++m) {
-            const float c = cf[m * kQPad];
-            const float4* xr = reinterpret_cast<const float4*>(sm + L::XT + m * S);
+        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+        const float2* cf = reinterpret_cast<const float2*>(M.Cf) + t;
+        float2 cur[U], nxt[U];
 #pragma unroll
-            for (int q = 0; q < S / 4; ++q) {
-                const float4 xv = xr[q];
-                acc[4 * q + 0] += c * xv.x; acc[4 * q + 1] += c * xv.y;
-                acc[4 * q + 2] += c * xv.z; acc[4 * q + 3] += c * xv.w;
+        for (int u = 0; u < U; ++u) { cur[u] = ld_const2(cf + u * NP); nxt[u] = cur[u]; }
+#pragma unroll 1
+        for (int m0 = 0; m0 < kXPad; m0 += U) {
+            if (m0 + U < kXPad) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = ld_const2(cf + (m0 + U + u) * NP);
             }
-        }
-        float4* qo = reinterpret_cast<float4*>(sm + L::QT + n * L::LDQ);
 #pragma unroll
-        for (int q = 0; q < S / 4; ++q) qo[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int u = 0; u < U; ++u) {
+                const float4* xr = reinterpret_cast<const float4*>(sm + L::XT + (m0 + u) * S);
+#pragma unroll
+                for (int q = 0; q < S / 4; ++q) {
+                    const float4 xv = xr[q];
+                    a0[4 * q + 0] += cur[u].x * xv.x; a0[4 * q + 1] += cur[u].x * xv.y;
+                    a0[4 * q + 2] += cur[u].x * xv.z; a0[4 * q + 3] += cur[u].x * xv.w;
+                    a1[4 * q + 0] += cur[u].y * xv.x; a1[4 * q + 1] += cur[u].y * xv.y;
+                    a1[4 * q + 2] += cur[u].y * xv.z; a1[4 * q + 3] += cur[u].y * xv.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        }
+        float4* q0 = reinterpret_cast<float4*>(sm + L::QT + (2 * t) * L::LDQ);
+        float4* q1 = reinterpret_cast<float4*>(sm + L::QT + (2 * t + 1) * L::LDQ);
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) {
+            q0[q] = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
+            q1[q] = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+        }
     }
 }
 
-// dx[m][s] = sum_n Cf[m][n] * dQ[n][s]   (transpose GEMM; result overwrites XT)
+// dx[m][s] = sum_n Cf[m][n] * dQ[n][s]   (transpose GEMM; result overwrites XT).
+// Device fast path (needs >= 384 threads): thread = (n-range r of 3, column pair mp of 112); the three
+// partial sums are combined in a fixed order through the (by then dead) QT region - deterministic.
 template <int S>
 SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
-    constexpr int H = (S % 8 == 0) ? 2 : 1;    // sample halves per row of x
-    constexpr int SH = S / H;
-    FOR_ITEMS(it, kXPad * H) {
-        const int m = it % kXPad, h = it / kXPad;
-        float acc[SH];
+    constexpr int U = 8, MP = kXPad / 2, NR = 3, NPER = (kQ + NR - 1) / NR;   // 227 rows per range
+    static_assert(NR * NPER <= kQPad, "ranges stay inside the padded rows");
+#if defined(__CUDA_ARCH__)
+    if (TILE_NT >= 128 * NR) {
+        const int tid = TILE_TID, r = tid >> 7, mp = tid & 127;
+        const bool active = (r < NR) && (mp < MP);
+        float a0[S], a1[S];
 #pragma unroll
-        for (int s = 0; s < SH; ++s) acc[s] = 0.f;
-        const float* ct = M.CfT + m;
-#pragma unroll 4
-        for (int n = 0; n < kQ; ++n) {
-            const float c = ct[n * kXPad];
-            const float4* qr = reinterpret_cast<const float4*>(sm + L::QT + n * L::LDQ + h * SH);
+        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+        if (active) {
+            const int n_begin = r * NPER, n_end = n_begin + NPER;     // rows >= kQ are zero in CfT
+            const float2* ct = reinterpret_cast<const float2*>(M.CfT) + mp;
+            float2 cur[U], nxt[U];
 #pragma unroll
-            for (int q = 0; q < SH / 4; ++q) {
-                const float4 v = qr[q];
-                acc[4 * q + 0] += c * v.x; acc[4 * q + 1] += c * v.y;
-                acc[4 * q + 2] += c * v.z; acc[4 * q + 3] += c * v.w;
+            for (int u = 0; u < U; ++u) { cur[u] = ld_const2(ct + (n_begin + u) * MP); nxt[u] = cur[u]; }
+#pragma unroll 1
+            for (int n0 = n_begin; n0 < n_end; n0 += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int nn = n0 + U + u;
+                    nxt[u] = (nn < n_end) ? ld_const2(ct + nn * MP) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (n0 + u < n_end) {
+                        const float4* qr = reinterpret_cast<const float4*>(sm + L::QT + (n0 + u) * L::LDQ);
+#pragma unroll
+                        for (int q = 0; q < S / 4; ++q) {
+                            const float4 v = qr[q];
+                            a0[4 * q + 0] += cur[u].x * v.x; a0[4 * q + 1] += cur[u].x * v.y;
+                            a0[4 * q + 2] += cur[u].x * v.z; a0[4 * q + 3] += cur[u].x * v.w;
+                            a1[4 * q + 0] += cur[u].y * v.x; a1[4 * q + 1] += cur[u].y * v.y;
+                            a1[4 * q + 2] += cur[u].y * v.z; a1[4 * q + 3] += cur[u].y * v.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
             }
         }
-        float4* xo = reinterpret_cast<float4*>(sm + L::XT + m * S + h * SH);
+        TILE_SYNC();                               // everyone is done reading dQ: QT becomes scratch
+        if (active) {
+            float* dst = (r == 0) ? (sm + L::XT + (2 * mp) * S) : (sm + L::QT + ((r - 1) * kXPad + 2 * mp) * S);
+            float4* d0 = reinterpret_cast<float4*>(dst);
+            float4* d1 = reinterpret_cast<float4*>(dst + S);
 #pragma unroll
-        for (int q = 0; q < SH / 4; ++q) xo[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+            for (int q = 0; q < S / 4; ++q) {
+                d0[q] = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
+                d1[q] = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+            }
+        }
+        TILE_SYNC();
+        FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = (sm[L::XT + i] + sm[L::QT + i]) + sm[L::QT + kXPad * S + i];
+        return;
+    }
+#endif
+    // generic path (host emulation, or fewer than 384 threads)
+    FOR_ITEMS(m, kXPad) {
+        float acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = 0.f;
+        const float* ct = M.CfT + m;
+        for (int n = 0; n < kQ; ++n) {
+            const float c = ct[n * kXPad];
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[s] += c * sm[L::QT + n * L::LDQ + s];
+        }
+        TILE_SYNC_NONE();
+#pragma unroll
+        for (int s = 0; s < S; ++s) sm[L::XT + m * S + s] = acc[s];
     }
 }
 
 // One of the 54 source joints of sample s (chain joint, skinned picked vertex, folded extra joint).
 template <int S>
-SB_HD void source_joint(const ModelView& M, const float* sm, int src, int s, float* P) {
+SB_HD void source_joint(const SmallConsts& C, const float* sm, int src, int s, float* P) {
     using L = TileLayout<S>;
     if (src < kJoints) {
         P[0] = sm[L::GW + (src * 12 + 3) * S + s];
@@ -297,7 +394,7 @@ SB_HD void source_joint(const ModelView& M, const float* sm, int src, int s, flo
 #pragma unroll
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
         for (int j = 0; j < kJoints; ++j) {
-            const float w = M.Wp[p * kJoints + j];
+            const float w = C.Wp[p * kJoints + j];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -315,7 +412,7 @@ SB_HD void source_joint(const ModelView& M, const float* sm, int src, int s, flo
         for (int j = 0; j < kJoints; ++j) {
             const int qb = (k * kJoints + j) * 3;
             const float qx = sm[L::QT + (qb + 0) * L::LDQ + s], qy = sm[L::QT + (qb + 1) * L::LDQ + s], qz = sm[L::QT + (qb + 2) * L::LDQ + s];
-            const float w = M.wkj[k * kJoints + j];
+            const float w = C.wkj[k * kJoints + j];
             const float* G = sm + L::GW + (j * 12) * S + s;
             a0 += G[0 * S] * qx + G[1 * S] * qy + G[2 * S] * qz + sm[L::AT + (3 * j + 0) * S + s] * w;
             a1 += G[4 * S] * qx + G[5 * S] * qy + G[6 * S] * qz + sm[L::AT + (3 * j + 1) * S + s] * w;
@@ -327,12 +424,12 @@ SB_HD void source_joint(const ModelView& M, const float* sm, int src, int s, flo
 
 // The 49 output joints into OUTJ.
 template <int S>
-SB_HD void ph_output_joints(const ModelView& M, float* sm) {
+SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, kOut * S) {
         const int s = it % S, o = it / S;
         float P[3];
-        source_joint<S>(M, sm, M.joint_map[o], s, P);
+        source_joint<S>(C, sm, M.joint_map[o], s, P);
         sm[L::OUTJ + (3 * o + 0) * S + s] = P[0];
         sm[L::OUTJ + (3 * o + 1) * S + s] = P[1];
         sm[L::OUTJ + (3 * o + 2) * S + s] = P[2];
@@ -367,39 +464,60 @@ SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad)
 // ------------------------------------------------------------------------------------------------
 // priors (smplify/prior.py:181-196 merged max-mixture; losses.py:19-24 angle prior; shape prior)
 // ------------------------------------------------------------------------------------------------
+// Pd[(g,i)][s] = sum_j Psym_g[i][j] * bp[j][s] - (Psym_g mean_g)[i]   for all 8 components: an
+// [S x 72] . [72 x 576] GEMM streamed like the folded one (two adjacent i per thread).
 template <int S>
-SB_HD void ph_prior_quadratic(const ModelView& M, float* sm) {
+SB_HD void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
-    // contrib[(g,i)][s] = (sum_j Psym_g[i][j] * bp[j] - (Psym_g mean_g)[i]) * (bp[i] - mean_g[i])
-    FOR_ITEMS(it, kGauss * kPriorDim) {
-        const int g = it / kPriorDim, i = it % kPriorDim;
-        float acc[S];
+    constexpr int U = 8, IP = kPriorPad / 2;        // 36 column pairs per component
+    static_assert(kPriorPad % U == 0, "prior padding");
+    FOR_ITEMS(t, kGauss * IP) {
+        const int g = t / IP, ip = t % IP;
+        float a0[S], a1[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) acc[s] = 0.f;
-        const float* P = M.gmm_prec + g * kPriorDim * kPriorDim + i;
-#pragma unroll 3
-        for (int j = 0; j < kPriorDim; ++j) {
-            const float c = P[j * kPriorDim];
-            const float* bp = sm + L::POSE + (3 + j) * S;
+        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+        const float2* P = reinterpret_cast<const float2*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + ip;
+        float2 cur[U], nxt[U];
 #pragma unroll
-            for (int s = 0; s < S; ++s) acc[s] += c * bp[s];
+        for (int u = 0; u < U; ++u) { cur[u] = ld_const2(P + u * IP); nxt[u] = cur[u]; }
+#pragma unroll 1
+        for (int j0 = 0; j0 < kPriorPad; j0 += U) {
+            if (j0 + U < kPriorPad) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) nxt[u] = ld_const2(P + (j0 + U + u) * IP);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                // rows j >= 69 of Psym are zero; the pose rows they meet (first betas) are finite
+                const float4* br = reinterpret_cast<const float4*>(sm + L::POSE + (3 + j0 + u) * S);
+#pragma unroll
+                for (int q = 0; q < S / 4; ++q) {
+                    const float4 v = br[q];
+                    a0[4 * q + 0] += cur[u].x * v.x; a0[4 * q + 1] += cur[u].x * v.y;
+                    a0[4 * q + 2] += cur[u].x * v.z; a0[4 * q + 3] += cur[u].x * v.w;
+                    a1[4 * q + 0] += cur[u].y * v.x; a1[4 * q + 1] += cur[u].y * v.y;
+                    a1[4 * q + 2] += cur[u].y * v.z; a1[4 * q + 3] += cur[u].y * v.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
-        const float pm = M.gmm_pmean[it], mu = M.gmm_means[it];
+        const float pm0 = C.pmean[g * kPriorPad + 2 * ip], pm1 = C.pmean[g * kPriorPad + 2 * ip + 1];
+        float* o = sm + L::QT + (g * kPriorPad + 2 * ip) * S;
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-            sm[L::QT + it * S + s] = (acc[s] - pm) * (sm[L::POSE + (3 + i) * S + s] - mu);
+        for (int s = 0; s < S; ++s) { o[s] = a0[s] - pm0; o[S + s] = a1[s] - pm1; }
     }
 }
 
 template <int S>
-SB_HD void ph_prior_select(const ModelView& M, float* sm, float prior_w2, float angle_w2, float shape_w2,
-                           const int* angle_ids, const float* angle_signs) {
+SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, float prior_w2, float angle_w2, float shape_w2) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, kGauss * S) {
         const int s = it % S, g = it / S;
         float q = 0.f;
-        for (int i = 0; i < kPriorDim; ++i) q += sm[L::QT + (g * kPriorDim + i) * S + s];
-        sm[L::MISC + g * S + s] = 0.5f * q - M.gmm_lognll[g];
+        for (int i = 0; i < kPriorDim; ++i)
+            q += sm[L::QT + (g * kPriorPad + i) * S + s] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
+        sm[L::MISC + g * S + s] = 0.5f * q - C.lognll[g];
     }
     TILE_SYNC();
     FOR_ITEMS(s, S) {
@@ -413,7 +531,7 @@ SB_HD void ph_prior_select(const ModelView& M, float* sm, float prior_w2, float 
         sm[L::LOSSJ + 49 * S + s] = prior_w2 * bv;
         float ang = 0.f;
         for (int a = 0; a < 4; ++a) {
-            const float e = expf(sm[L::POSE + (3 + angle_ids[a]) * S + s] * angle_signs[a]);
+            const float e = expf(sm[L::POSE + (3 + M.angle_ids[a]) * S + s] * M.angle_signs[a]);
             ang += e * e;
         }
         sm[L::LOSSJ + 50 * S + s] = angle_w2 * ang;
@@ -426,14 +544,11 @@ SB_HD void ph_prior_select(const ModelView& M, float* sm, float prior_w2, float 
     FOR_ITEMS(it, kPriorDim * S) {
         const int s = it % S, i = it / S;
         const int g = (int)sm[L::MISC + 8 * S + s];
-        const float* P = M.gmm_prec + g * kPriorDim * kPriorDim + i;
-        float a = 0.f;
-        for (int j = 0; j < kPriorDim; ++j) a += P[j * kPriorDim] * sm[L::POSE + (3 + j) * S + s];
-        float gr = prior_w2 * (a - M.gmm_pmean[g * kPriorDim + i]);
+        float gr = prior_w2 * sm[L::QT + (g * kPriorPad + i) * S + s];
         for (int k = 0; k < 4; ++k)
-            if (angle_ids[k] == i) {
-                const float e = expf(sm[L::POSE + (3 + i) * S + s] * angle_signs[k]);
-                gr += angle_w2 * 2.0f * angle_signs[k] * e * e;
+            if (M.angle_ids[k] == i) {
+                const float e = expf(sm[L::POSE + (3 + i) * S + s] * M.angle_signs[k]);
+                gr += angle_w2 * 2.0f * M.angle_signs[k] * e * e;
             }
         sm[L::GPR + i * S + s] = gr;
     }
@@ -460,7 +575,7 @@ SB_HD void source_grad(const ModelView& M, const float* sm, int src, int s, floa
 // dL/dA_j from the extra joints and the picked vertices, converted to dL/dG_j and dL/dJ_j.
 // extern_dA (may be null): additional dL/dA [24][12] rows per sample coming from the vertex path.
 template <int S>
-SB_HD void ph_joint_backward(const ModelView& M, float* sm) {
+SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, kJoints * S) {
         const int s = it % S, j = it / S;
@@ -482,7 +597,7 @@ SB_HD void ph_joint_backward(const ModelView& M, float* sm) {
             float* q1 = sm + L::QT + (qb + 1) * L::LDQ + s;
             float* q2 = sm + L::QT + (qb + 2) * L::LDQ + s;
             const float qx = *q0, qy = *q1, qz = *q2;
-            const float w = M.wkj[k * kJoints + j];
+            const float w = C.wkj[k * kJoints + j];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 dAR[r * 3 + 0] += dE[r] * qx; dAR[r * 3 + 1] += dE[r] * qy; dAR[r * 3 + 2] += dE[r] * qz;
@@ -495,7 +610,7 @@ SB_HD void ph_joint_backward(const ModelView& M, float* sm) {
         for (int p = 0; p < kPicks; ++p) {
             float dV[3];
             source_grad<S>(M, sm, kJoints + p, s, dV);
-            const float w = M.Wp[p * kJoints + j];
+            const float w = C.Wp[p * kJoints + j];
             const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
                         vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
 #pragma unroll
@@ -524,7 +639,7 @@ SB_HD void ph_joint_backward(const ModelView& M, float* sm) {
 
 // dL/d(v_posed of picked vertex) = (sum_j Wp[p][j] G_j^R)^T dL/dvert ; written over the pick rows of QT.
 template <int S>
-SB_HD void ph_pick_backward(const ModelView& M, float* sm) {
+SB_HD void ph_pick_backward(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, kPicks * S) {
         const int s = it % S, p = it / S;
@@ -534,7 +649,7 @@ SB_HD void ph_pick_backward(const ModelView& M, float* sm) {
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
         for (int j = 0; j < kJoints; ++j) {
-            const float w = M.Wp[p * kJoints + j];
+            const float w = C.Wp[p * kJoints + j];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -639,10 +754,10 @@ SB_HD void rotation_grad(const float* sm, int j, int s, float* g) {
 
 // dL/dbeta_l = dx[1+l] + sum_{j,c} JS[j][c][l] dJ[j][c]  (the prior term is added by the caller)
 template <int S>
-SB_HD float beta_grad(const ModelView& M, const float* sm, int l, int s) {
+SB_HD float beta_grad(const SmallConsts& C, const float* sm, int l, int s) {
     using L = TileLayout<S>;
     float a = sm[L::XT + (1 + l) * S + s];
-    for (int jc = 0; jc < 72; ++jc) a += M.JS[jc * kBetas + l] * sm[L::DJ + jc * S + s];
+    for (int jc = 0; jc < 72; ++jc) a += C.JS[jc * kBetas + l] * sm[L::DJ + jc * S + s];
     return a;
 }
 

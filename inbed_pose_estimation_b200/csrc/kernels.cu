@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(const __gri
 }
 
 template <int S>
-static size_t tile_smem_bytes() { return (size_t)(TileLayout<S>::TOTAL + 2 * kMaxIters) * sizeof(float); }
+static size_t tile_smem_bytes() { return (size_t)TileLayout<S>::SMEM_FLOATS * sizeof(float); }
 
 template <typename K>
 static cudaError_t opt_in_smem(K kernel, size_t bytes) {

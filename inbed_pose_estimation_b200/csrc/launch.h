@@ -9,7 +9,7 @@ struct FitParams;
 struct PoseParams;
 
 constexpr int kFitThreads = 384;
-constexpr int kPoseThreads = 256;
+constexpr int kPoseThreads = 384;
 constexpr int kMaxSplit = 8;
 
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream);

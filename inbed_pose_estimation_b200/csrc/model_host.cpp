@@ -190,22 +190,22 @@ std::string build_host_model(const smplb200_model_desc& d, HostModel& H) {
 
     // ---- max-mixture prior ------------------------------------------------------------------------------
     H.has_prior = d.gmm_means && d.gmm_precisions && d.gmm_nll_weights;
-    H.gmm_means.assign(kGauss * kPriorDim, 0.f);
-    H.gmm_prec.assign((size_t)kGauss * kPriorDim * kPriorDim, 0.f);
-    H.gmm_pmean.assign(kGauss * kPriorDim, 0.f);
+    H.gmm_means.assign(kGauss * kPriorPad, 0.f);
+    H.gmm_prec.assign((size_t)kGauss * kPriorPad * kPriorPad, 0.f);
+    H.gmm_pmean.assign(kGauss * kPriorPad, 0.f);
     H.gmm_lognll.assign(kGauss, 0.f);
     if (H.has_prior) {
-        memcpy(H.gmm_means.data(), d.gmm_means, sizeof(float) * kGauss * kPriorDim);
         for (int g = 0; g < kGauss; ++g) {
+            for (int i = 0; i < kPriorDim; ++i) H.gmm_means[g * kPriorPad + i] = d.gmm_means[g * kPriorDim + i];
             const float* P = d.gmm_precisions + (size_t)g * kPriorDim * kPriorDim;
-            float* Ps = H.gmm_prec.data() + (size_t)g * kPriorDim * kPriorDim;
+            float* Ps = H.gmm_prec.data() + (size_t)g * kPriorPad * kPriorPad;
             for (int i = 0; i < kPriorDim; ++i)
                 for (int j = 0; j < kPriorDim; ++j)   // d^T P d == d^T Psym d ; gradient 0.5 (P + P^T) d == Psym d
-                    Ps[j * kPriorDim + i] = (float)(0.5 * ((double)P[i * kPriorDim + j] + (double)P[j * kPriorDim + i]));
+                    Ps[j * kPriorPad + i] = (float)(0.5 * ((double)P[i * kPriorDim + j] + (double)P[j * kPriorDim + i]));
             for (int i = 0; i < kPriorDim; ++i) {
                 double a = 0.0;
-                for (int j = 0; j < kPriorDim; ++j) a += (double)Ps[j * kPriorDim + i] * (double)d.gmm_means[g * kPriorDim + j];
-                H.gmm_pmean[g * kPriorDim + i] = (float)a;
+                for (int j = 0; j < kPriorDim; ++j) a += (double)Ps[j * kPriorPad + i] * (double)d.gmm_means[g * kPriorDim + j];
+                H.gmm_pmean[g * kPriorPad + i] = (float)a;
             }
             if (!(d.gmm_nll_weights[g] > 0.f)) return "gmm_nll_weights must be positive (representable in fp32)";
             H.gmm_lognll[g] = (float)log((double)d.gmm_nll_weights[g]);

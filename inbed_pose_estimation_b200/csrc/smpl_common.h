@@ -31,6 +31,7 @@ constexpr int kOut = 49;             // joints after joint_map
 constexpr int kSrc = 54;             // 24 chain + 21 selected vertices + 9 extra
 constexpr int kGauss = 8;
 constexpr int kPriorDim = 69;
+constexpr int kPriorPad = 72;         // padded row/column count of the prior matrices
 constexpr int kParams = 82;          // 72 pose + 10 betas
 constexpr int kMaxLevels = 24;
 
@@ -45,9 +46,9 @@ struct ModelView {
     const float* Wp;         // [11][24]           skinning weights of the picked vertices
     const float* J0;         // [24][3]            J_regressor . v_template
     const float* JS;         // [24][3][10]        J_regressor . shapedirs
-    const float* gmm_means;  // [8][69]
-    const float* gmm_prec;   // [8][69 j][69 i]    symmetrised precision, i fastest
-    const float* gmm_pmean;  // [8][69]            prec_sym . mean
+    const float* gmm_means;  // [8][72]            zero padded
+    const float* gmm_prec;   // [8][72 j][72 i]    symmetrised precision, i fastest, zero padded
+    const float* gmm_pmean;  // [8][72]            prec_sym . mean
     const float* gmm_lognll; // [8]                log(nll_weights)
     int32_t pick_vid[kSelVerts];
     int8_t parents[kJoints];

@@ -64,17 +64,19 @@ class _SMPLFunction(torch.autograd.Function):
         betas_c = betas.detach().contiguous().float()
         verts = torch.empty((B, constants.NUM_VERTS, 3), device=dev, dtype=torch.float32) if need_vertices else None
         joints = torch.empty((B, constants.NUM_JOINTS_OUT, 3), device=dev, dtype=torch.float32)
-        needs_grad = torch.is_grad_enabled() and (pose.requires_grad or betas.requires_grad)
+        needs_grad = bool(ctx.needs_input_grad[1] or ctx.needs_input_grad[2])   # forward runs under no_grad
         vposed = torch.empty_like(verts) if (needs_grad and need_vertices) else None
         ws = module.workspace(dev, B)
         with torch.cuda.device(dev):
-            _native.check(lib.smplb200_smpl_forward(
-                native.handle, B, int(rotmat_mode), _native.ptr(pose_c), _native.ptr(betas_c), _native.ptr(verts),
-                _native.ptr(joints), _native.ptr(vposed), ws.data_ptr(), ws.numel(),
-                torch.cuda.current_stream(dev).cuda_stream))
+            if B > 0:
+                _native.check(lib.smplb200_smpl_forward(
+                    native.handle, B, int(rotmat_mode), _native.ptr(pose_c), _native.ptr(betas_c), _native.ptr(verts),
+                    _native.ptr(joints), _native.ptr(vposed), ws.data_ptr(), ws.numel(),
+                    torch.cuda.current_stream(dev).cuda_stream))
         ctx.module, ctx.rotmat_mode, ctx.pose_shape = module, rotmat_mode, pose.shape
         ctx.save_for_backward(pose_c, betas_c, vposed if vposed is not None else torch.empty(0, device=dev))
         ctx.has_vposed = vposed is not None
+        ctx.wanted_vertices = bool(need_vertices)
         if verts is None:
             verts = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(verts)
@@ -88,10 +90,14 @@ class _SMPLFunction(torch.autograd.Function):
         dev = betas_c.device
         lib = _native.lib()
         gv = g_verts.contiguous().float() if (g_verts is not None and ctx.has_vposed) else None
+        if g_verts is not None and g_verts.numel() > 0 and not ctx.has_vposed and ctx.wanted_vertices:
+            raise RuntimeError('SMPL backward: vertex gradient arrived but v_posed was not saved')
         gj = g_joints.contiguous().float() if g_joints is not None else None
         d_pose = torch.empty_like(pose_c)
         d_betas = torch.empty_like(betas_c)
         ws = module.workspace(dev, B)
+        if B == 0:
+            return None, d_pose.view(ctx.pose_shape), d_betas, None, None
         with torch.cuda.device(dev):
             _native.check(lib.smplb200_smpl_backward(
                 module.native(dev).handle, B, int(ctx.rotmat_mode), _native.ptr(pose_c), _native.ptr(betas_c),

@@ -77,6 +77,9 @@ class SMPLify(object):
         vertices, joints = new(B, constants.NUM_VERTS, 3), new(B, constants.NUM_JOINTS_OUT, 3)
         o_pose, o_betas, o_cam, reproj = new(B, 72), new(B, 10), new(B, 3), new(B, constants.NUM_JOINTS_OUT)
         trace = new(2 * self.num_iters, B) if return_loss_trace else None
+        self.last_loss_trace = trace
+        if B == 0:
+            return vertices, joints, o_pose, o_betas, o_cam, reproj
         ws = self._workspace(B)
         with torch.cuda.device(dev):
             _native.check(_native.lib().smplb200_smplify_fit(
@@ -100,6 +103,8 @@ class SMPLify(object):
         cen = self._prep(camera_center, (B, 2), 'camera_center')
         kp, writeback = self._keypoints(keypoints_2d, B)
         reproj = torch.empty((B, constants.NUM_JOINTS_OUT), device=self._dev, dtype=torch.float32)
+        if B == 0:
+            return reproj
         ws = self._workspace(B)
         with torch.cuda.device(self._dev):
             _native.check(_native.lib().smplb200_smplify_fitting_loss(
