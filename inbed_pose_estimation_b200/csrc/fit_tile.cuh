@@ -253,117 +253,167 @@ SB_HD void ph_chain_forward(const ModelView& M, float* sm) {
     }
 }
 
+SB_HD float4 ld_const4(const float4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// 4-column x 8-sample register tile, acc[c][s] += w[c] * v[s].  On the device the samples are packed in
+// pairs and updated with Blackwell's packed fp32 FMA (fma.rn.f32x2 via __ffma2_rn): scalar FFMA issues at
+// half rate on sm_100, the 2-wide form is what reaches the fp32 peak.  Results are bit-identical to scalar fmaf.
+struct Tile4x8 {
+#if defined(__CUDA_ARCH__)
+    float2 a[4][4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a[c][p] = make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ void fma(const float4& w, const float4& v0, const float4& v1) {
+        const float2 vp[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+        const float2 wp[4] = {make_float2(w.x, w.x), make_float2(w.y, w.y), make_float2(w.z, w.z), make_float2(w.w, w.w)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a[c][p] = __ffma2_rn(wp[c], vp[p], a[c][p]);
+    }
+    __device__ __forceinline__ float4 lo(int c) const { return make_float4(a[c][0].x, a[c][0].y, a[c][1].x, a[c][1].y); }
+    __device__ __forceinline__ float4 hi(int c) const { return make_float4(a[c][2].x, a[c][2].y, a[c][3].x, a[c][3].y); }
+#else
+    float a[4][8];
+    void clear() {
+        for (int c = 0; c < 4; ++c)
+            for (int s = 0; s < 8; ++s) a[c][s] = 0.f;
+    }
+    void fma(const float4& w, const float4& v0, const float4& v1) {
+        const float ww[4] = {w.x, w.y, w.z, w.w};
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        for (int c = 0; c < 4; ++c)
+            for (int s = 0; s < 8; ++s) a[c][s] = fmaf(ww[c], vv[s], a[c][s]);
+    }
+    float4 lo(int c) const { return make_float4(a[c][0], a[c][1], a[c][2], a[c][3]); }
+    float4 hi(int c) const { return make_float4(a[c][4], a[c][5], a[c][6], a[c][7]); }
+#endif
+};
+
 // QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
-// One thread owns two adjacent columns for all S samples (2S accumulators); the basis rows are
-// streamed from L2 with U rows in flight per thread, x is broadcast from shared memory.
+// S % 8 == 0: one thread owns 4 adjacent columns x 8 samples (32 accumulators, 1 LDG.128 + 2 LDS.128 per
+// 32 FMAs); the basis rows are streamed from L2 two groups of U rows ahead, x is broadcast from smem.
 template <int S>
 SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
-    constexpr int U = 8, NP = kQPad / 2;
-    static_assert(kXPad % U == 0, "k padding");
-    FOR_ITEMS(t, NP) {
-        float a0[S], a1[S];
+    if constexpr (S % 8 == 0) {
+        constexpr int U = 4, NQ4 = kQPad / 4, H = S / 8;       // 176 column quads, H sample groups
+        static_assert(kXPad % U == 0, "k padding");
+        FOR_ITEMS(t, NQ4 * H) {
+            const int cq = t % NQ4, h = t / NQ4;
+            Tile4x8 acc;
+            acc.clear();
+            const float4* cf = reinterpret_cast<const float4*>(M.Cf) + cq;
+            const float* xb = sm + L::XT + 8 * h;
+            float4 c0[U], c1[U], c2[U];
 #pragma unroll
-        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
-        const float2* cf = reinterpret_cast<const float2*>(M.Cf) + t;
-        float2 cur[U], nxt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { cur[u] = ld_const2(cf + u * NP); nxt[u] = cur[u]; }
+            for (int u = 0; u < U; ++u) { c0[u] = ld_const4(cf + u * NQ4); c1[u] = ld_const4(cf + (U + u) * NQ4); c2[u] = c1[u]; }
 #pragma unroll 1
-        for (int m0 = 0; m0 < kXPad; m0 += U) {
-            if (m0 + U < kXPad) {
+            for (int m0 = 0; m0 < kXPad; m0 += U) {
+                if (m0 + 2 * U < kXPad) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) nxt[u] = ld_const2(cf + (m0 + U + u) * NP);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float4* xr = reinterpret_cast<const float4*>(sm + L::XT + (m0 + u) * S);
-#pragma unroll
-                for (int q = 0; q < S / 4; ++q) {
-                    const float4 xv = xr[q];
-                    a0[4 * q + 0] += cur[u].x * xv.x; a0[4 * q + 1] += cur[u].x * xv.y;
-                    a0[4 * q + 2] += cur[u].x * xv.z; a0[4 * q + 3] += cur[u].x * xv.w;
-                    a1[4 * q + 0] += cur[u].y * xv.x; a1[4 * q + 1] += cur[u].y * xv.y;
-                    a1[4 * q + 2] += cur[u].y * xv.z; a1[4 * q + 3] += cur[u].y * xv.w;
+                    for (int u = 0; u < U; ++u) c2[u] = ld_const4(cf + (m0 + 2 * U + u) * NQ4);
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float4* xr = reinterpret_cast<const float4*>(xb + (m0 + u) * S);
+                    const float4 v0 = xr[0], v1 = xr[1];
+                    acc.fma(c0[u], v0, v1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) { c0[u] = c1[u]; c1[u] = c2[u]; }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            for (int c = 0; c < 4; ++c) {
+                float4* qo = reinterpret_cast<float4*>(sm + L::QT + (4 * cq + c) * L::LDQ + 8 * h);
+                qo[0] = acc.lo(c);
+                qo[1] = acc.hi(c);
+            }
         }
-        float4* q0 = reinterpret_cast<float4*>(sm + L::QT + (2 * t) * L::LDQ);
-        float4* q1 = reinterpret_cast<float4*>(sm + L::QT + (2 * t + 1) * L::LDQ);
+    } else {
+        FOR_ITEMS(n, kQPad) {
+            float a[S];
 #pragma unroll
-        for (int q = 0; q < S / 4; ++q) {
-            q0[q] = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
-            q1[q] = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+            for (int s = 0; s < S; ++s) a[s] = 0.f;
+            for (int m = 0; m < kX; ++m) {
+                const float c = M.Cf[m * kQPad + n];
+#pragma unroll
+                for (int s = 0; s < S; ++s) a[s] += c * sm[L::XT + m * S + s];
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) sm[L::QT + n * L::LDQ + s] = a[s];
         }
     }
 }
 
 // dx[m][s] = sum_n Cf[m][n] * dQ[n][s]   (transpose GEMM; result overwrites XT).
-// Device fast path (needs >= 384 threads): thread = (n-range r of 3, column pair mp of 112); the three
-// partial sums are combined in a fixed order through the (by then dead) QT region - deterministic.
+// Device fast path (S % 8 == 0, >= 384 threads): thread = (n-range r of 3, sample group h, column quad mq of
+// 56), 4 x 8 accumulators; the three partial sums are combined in a fixed order through the (by then dead)
+// QT region - deterministic, no atomics.
 template <int S>
 SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
-    constexpr int U = 8, MP = kXPad / 2, NR = 3, NPER = (kQ + NR - 1) / NR;   // 227 rows per range
-    static_assert(NR * NPER <= kQPad, "ranges stay inside the padded rows");
 #if defined(__CUDA_ARCH__)
-    if (TILE_NT >= 128 * NR) {
-        const int tid = TILE_TID, r = tid >> 7, mp = tid & 127;
-        const bool active = (r < NR) && (mp < MP);
-        float a0[S], a1[S];
+    if constexpr (S % 8 == 0) {
+        constexpr int U = 4, MQ = kXPad / 4, H = S / 8, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
+        static_assert(NR * NPER <= kQPad && NR * NPER >= kQ && NPER % U == 0, "n ranges");
+        constexpr int PER_R = MQ * H;                                          // 112 threads per range when S = 16
+        if (TILE_NT >= PER_R * NR) {
+            const int tid = TILE_TID, r = tid / PER_R, w = tid % PER_R, mq = w % MQ, h = w / MQ;
+            const bool active = r < NR;
+            Tile4x8 acc;
+            acc.clear();
+            if (active) {
+                const int n_begin = r * NPER;
+                const float4* ct = reinterpret_cast<const float4*>(M.CfT) + (size_t)n_begin * MQ + mq;
+                const float* qb = sm + L::QT + n_begin * L::LDQ + 8 * h;
+                float4 c0[U], c1[U], c2[U];
 #pragma unroll
-        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
-        if (active) {
-            const int n_begin = r * NPER, n_end = n_begin + NPER;     // rows >= kQ are zero in CfT
-            const float2* ct = reinterpret_cast<const float2*>(M.CfT) + mp;
-            float2 cur[U], nxt[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { cur[u] = ld_const2(ct + (n_begin + u) * MP); nxt[u] = cur[u]; }
+                for (int u = 0; u < U; ++u) { c0[u] = ld_const4(ct + u * MQ); c1[u] = ld_const4(ct + (U + u) * MQ); c2[u] = c1[u]; }
 #pragma unroll 1
-            for (int n0 = n_begin; n0 < n_end; n0 += U) {
+                for (int n0 = 0; n0 < NPER; n0 += U) {
+                    if (n0 + 2 * U < NPER) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int nn = n0 + U + u;
-                    nxt[u] = (nn < n_end) ? ld_const2(ct + nn * MP) : make_float2(0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (n0 + u < n_end) {
-                        const float4* qr = reinterpret_cast<const float4*>(sm + L::QT + (n0 + u) * L::LDQ);
-#pragma unroll
-                        for (int q = 0; q < S / 4; ++q) {
-                            const float4 v = qr[q];
-                            a0[4 * q + 0] += cur[u].x * v.x; a0[4 * q + 1] += cur[u].x * v.y;
-                            a0[4 * q + 2] += cur[u].x * v.z; a0[4 * q + 3] += cur[u].x * v.w;
-                            a1[4 * q + 0] += cur[u].y * v.x; a1[4 * q + 1] += cur[u].y * v.y;
-                            a1[4 * q + 2] += cur[u].y * v.z; a1[4 * q + 3] += cur[u].y * v.w;
-                        }
+                        for (int u = 0; u < U; ++u) c2[u] = ld_const4(ct + (n0 + 2 * U + u) * MQ);
                     }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const float4* qr = reinterpret_cast<const float4*>(qb + (n0 + u) * L::LDQ);
+                        const float4 v0 = qr[0], v1 = qr[1];
+                        acc.fma(c0[u], v0, v1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { c0[u] = c1[u]; c1[u] = c2[u]; }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
             }
-        }
-        TILE_SYNC();                               // everyone is done reading dQ: QT becomes scratch
-        if (active) {
-            float* dst = (r == 0) ? (sm + L::XT + (2 * mp) * S) : (sm + L::QT + ((r - 1) * kXPad + 2 * mp) * S);
-            float4* d0 = reinterpret_cast<float4*>(dst);
-            float4* d1 = reinterpret_cast<float4*>(dst + S);
+            TILE_SYNC();                               // everyone is done reading dQ: QT becomes scratch
+            if (active) {
+                float* dst = (r == 0) ? (sm + L::XT) : (sm + L::QT + (r - 1) * kXPad * S);
 #pragma unroll
-            for (int q = 0; q < S / 4; ++q) {
-                d0[q] = make_float4(a0[4 * q], a0[4 * q + 1], a0[4 * q + 2], a0[4 * q + 3]);
-                d1[q] = make_float4(a1[4 * q], a1[4 * q + 1], a1[4 * q + 2], a1[4 * q + 3]);
+                for (int c = 0; c < 4; ++c) {
+                    float4* d = reinterpret_cast<float4*>(dst + (4 * mq + c) * S + 8 * h);
+                    d[0] = acc.lo(c);
+                    d[1] = acc.hi(c);
+                }
             }
+            TILE_SYNC();
+            FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = (sm[L::XT + i] + sm[L::QT + i]) + sm[L::QT + kXPad * S + i];
+            return;
         }
-        TILE_SYNC();
-        FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = (sm[L::XT + i] + sm[L::QT + i]) + sm[L::QT + kXPad * S + i];
-        return;
     }
 #endif
-    // generic path (host emulation, or fewer than 384 threads)
+    // generic path (host emulation, small S, or too few threads)
     FOR_ITEMS(m, kXPad) {
         float acc[S];
 #pragma unroll
@@ -374,7 +424,6 @@ SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
 #pragma unroll
             for (int s = 0; s < S; ++s) acc[s] += c * sm[L::QT + n * L::LDQ + s];
         }
-        TILE_SYNC_NONE();
 #pragma unroll
         for (int s = 0; s < S; ++s) sm[L::XT + m * S + s] = acc[s];
     }

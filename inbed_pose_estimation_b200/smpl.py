@@ -163,13 +163,9 @@ class SMPL(torch.nn.Module):
             raise ValueError('global_orient, body_pose and betas are required')
         B = betas.shape[0]
         if pose2rot:
-            full_pose = torch.cat([global_orient.reshape(B, -1), body_pose.reshape(B, -1)], dim=1)
-            if full_pose.shape[1] != 72:
-                raise ValueError('axis-angle pose must have 72 entries, got %d' % full_pose.shape[1])
+            full_pose = torch.cat([global_orient.reshape(B, 3), body_pose.reshape(B, 69)], dim=1)
         else:
-            full_pose = torch.cat([global_orient.reshape(B, -1, 3, 3), body_pose.reshape(B, -1, 3, 3)], dim=1)
-            if full_pose.shape[1] != 24:
-                raise ValueError('rotation-matrix pose must have 24 joints, got %d' % full_pose.shape[1])
+            full_pose = torch.cat([global_orient.reshape(B, 1, 3, 3), body_pose.reshape(B, 23, 3, 3)], dim=1)
         verts, joints = _SMPLFunction.apply(self, full_pose, betas, not pose2rot, bool(return_verts))
         return ModelOutput(vertices=verts if return_verts else None, joints=joints, betas=betas,
                            global_orient=global_orient, body_pose=body_pose,

@@ -24,7 +24,7 @@ def _build():
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    cmd = [nvcc, '-O2', '-std=c++17', '-DSMPLB200_EMU', '-Wno-deprecated-gpu-targets', '-shared', '-Xcompiler', '-fPIC',
+    cmd = [nvcc, '-O2', '-std=c++17', '-DSMPLB200_EMU', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC',
            '-o', LIB, os.path.join(HERE, 'emu_api.cu'), os.path.join(csrc, 'model_host.cpp')]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     if res.returncode != 0:

@@ -38,7 +38,7 @@ extern "C" EmuModel* emu_model_create(const smplb200_model_desc* d) {
 }
 extern "C" void emu_model_destroy(EmuModel* m) { delete m; }
 
-constexpr int S = 4;
+constexpr int S = 8;
 static std::vector<float> tile_scratch() { return std::vector<float>(TileLayout<S>::SMEM_FLOATS + 64, 0.f); }
 
 extern "C" int emu_fit(EmuModel* m, int batch, int num_iters, float step_size, float focal, int loss_only,

@@ -40,3 +40,27 @@ for r in rows:
 print('total samples', total)
 for (f, ln), (s, x, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print('%5.1f%% %9d inst  %s:%d  %s' % (100.0 * s / max(total, 1), x, f, ln, src))
+
+# ---- aggregate per enclosing function (by line ranges of "SB_HD ... name(" definitions) ----
+import os, re
+root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'inbed_pose_estimation_b200', 'csrc')
+funcs = {}
+for fn in os.listdir(root):
+    if not fn.endswith(('.cuh', '.cu', '.h')):
+        continue
+    starts = []
+    for i, line in enumerate(open(os.path.join(root, fn)), 1):
+        m = re.match(r'^(?:SB_HD|__global__|static|template|inline|cudaError_t)?.*?\b([A-Za-z_0-9]+)\s*\((?:const|float|int|bool|ModelView|FitParams|PoseParams)', line)
+        if m and not line.startswith((' ', '\t', '//', '#')) and '(' in line and ';' not in line:
+            starts.append((i, m.group(1)))
+    funcs[fn] = starts
+per = defaultdict(int)
+for (f, ln), (s, x, src) in agg.items():
+    name = '?'
+    for st, nm in funcs.get(f, []):
+        if st <= ln:
+            name = nm
+    per[(f, name)] += s
+print('\nper function:')
+for (f, name), s in sorted(per.items(), key=lambda kv: -kv[1])[:25]:
+    print('%5.1f%%  %s:%s' % (100.0 * s / max(total, 1), f, name))
