@@ -18,7 +18,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsmplify_b200.so')
-SOURCES = ['kernels.cu', 'api.cu', 'model_host.cpp']
+SOURCES = ['kernels.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -152,6 +152,8 @@ def _declare(lib):
     lib.smplb200_perspective_projection.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp]
     lib.smplb200_perspective_projection_backward.restype = ci
     lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+    lib.smplb200_probe_fp32_peak.restype = ci
+    lib.smplb200_probe_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.smplb200_smplify_fit_host.restype = ci
     lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
     return lib
@@ -162,7 +164,7 @@ EXPORTED_SYMBOLS = (
     'smplb200_fit_workspace_bytes', 'smplb200_smpl_workspace_bytes', 'smplb200_smplify_fit',
     'smplb200_smplify_fitting_loss', 'smplb200_smpl_forward', 'smplb200_smpl_backward',
     'smplb200_batch_rodrigues', 'smplb200_batch_rodrigues_backward', 'smplb200_perspective_projection',
-    'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count',
+    'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count', 'smplb200_probe_fp32_peak',
 )
 
 

@@ -1,0 +1,77 @@
+"""Sharded bulk refit (BASELINE config 4): every sample's fit is independent, so the batch is split
+contiguously over the ranks of a torch.distributed group, fitted locally with no inner-loop traffic,
+and the packed results are all-gathered once (pose 72 + betas 10 + camera 3 + reprojection 49 floats
+per sample).  The keep-if-better rule is the reference's (train/trainer.py:716-727)."""
+import torch
+import torch.distributed as dist
+
+PACKED = 72 + 10 + 3 + 49
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous rows [lo, hi) of rank `rank` when n rows are split over `world` ranks."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_results(pose, betas, cam_t, reproj):
+    return torch.cat([pose, betas, cam_t, reproj], dim=1)
+
+
+def unpack_results(packed):
+    return packed[:, :72], packed[:, 72:82], packed[:, 82:85], packed[:, 85:]
+
+
+def gather_rows(local, n_total, group=None):
+    """All-gather a [n_local, C] tensor whose row counts follow shard_bounds -> [n_total, C] on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(n_total, world, r) for r in range(world)]
+    max_rows = max(hi - lo for lo, hi in sizes)
+    padded = local.new_zeros((max_rows, local.shape[1]))
+    padded[:local.shape[0]] = local
+    out = local.new_empty((world * max_rows, local.shape[1]))
+    dist.all_gather_into_tensor(out, padded, group=group)
+    rows = [out[r * max_rows:r * max_rows + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    assert rows[rank].shape[0] == local.shape[0]
+    return torch.cat(rows, dim=0)
+
+
+def keep_if_better(old_fits, old_loss, new_fits, new_loss):
+    """update = new_loss < old_loss (trainer.py:719); masked overwrite (:722-727)."""
+    update = new_loss < old_loss
+    fits = torch.where(update[:, None], new_fits, old_fits)
+    loss = torch.where(update, new_loss, old_loss)
+    return fits, loss, update
+
+
+class ShardedRefit(object):
+    """refit(fits [N,82], cam_t [N,3], center [N,2], keypoints [N,49,3], old_loss [N]) on every rank.
+
+    `fit_fn(pose, betas, cam_t, center, keypoints)` must return the SMPLify 6-tuple for its rows; it
+    defaults to the CUDA SMPLify passed in.  Returns (fits [N,82], loss [N], updated [N] bool, cam_t [N,3]),
+    identical on all ranks."""
+
+    def __init__(self, smplify=None, fit_fn=None, group=None, device=None):
+        self.fit_fn = fit_fn if fit_fn is not None else smplify
+        self.group = group
+        self.device = device if device is not None else (smplify.device if smplify is not None else None)
+
+    def __call__(self, fits, cam_t, center, keypoints, old_loss):
+        n = fits.shape[0]
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        lo, hi = shard_bounds(n, world, rank)
+        dev = self.device if self.device is not None else fits.device
+        sl = lambda t: t[lo:hi].to(dev, non_blocking=True).contiguous()
+        out = self.fit_fn(sl(fits[:, :72]), sl(fits[:, 72:]), sl(cam_t), sl(center), sl(keypoints).clone())
+        _, _, pose, betas, cam, reproj = out
+        packed = gather_rows(pack_results(pose, betas, cam.detach(), reproj), n, self.group)
+        pose, betas, cam, reproj = unpack_results(packed)
+        new_loss = reproj.mean(dim=-1)                       # trainer.py:716
+        new_fits = torch.cat([pose, betas], dim=1)
+        fits_d, loss_d, update = keep_if_better(fits.to(packed.device), old_loss.to(packed.device), new_fits, new_loss)
+        return fits_d, loss_d, update, cam

@@ -137,6 +137,10 @@ int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_it
  * (bench.py reports it as gpu_launches). */
 long long smplb200_launch_count(int reset);
 
+/* Measures the fp32 FMA rate of the CUDA-core pipes on the current device (packed = 0: scalar FFMA,
+ * 1: Blackwell packed FFMA2) - the roofline denominator bench.py uses for the SIMT-bound fit kernel. */
+int smplb200_probe_fp32_peak(int packed, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif
