@@ -18,7 +18,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.path.join(_HERE, 'libsmplify_b200.so')
-SOURCES = ['kernels.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
+SOURCES = ['kernels.cu', 'lbs_tc.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 

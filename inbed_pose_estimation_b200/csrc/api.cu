@@ -11,7 +11,9 @@
 #include "../../include/smplify_b200.h"
 #include "fit_driver.cuh"
 #include "launch.h"
+#include "lbs_tc.h"
 #include "model_host.h"
+#include <stdlib.h>
 
 using namespace smplb200;
 
@@ -19,6 +21,8 @@ struct smplb200_model {
     int device = 0;
     ModelView view;
     bool has_prior = false;
+    bool tc_ok = false;            // tcgen05 vertex kernel usable (tensor maps encoded)
+    TcMaps tc_maps;
     std::vector<void*> allocations;
     // grow-only device scratch + pinned staging of the host-buffer entry point
     std::mutex mu;
@@ -97,6 +101,17 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
     rc |= upload(m, H.gmm_prec, &m->view.gmm_prec);
     rc |= upload(m, H.gmm_pmean, &m->view.gmm_pmean);
     rc |= upload(m, H.gmm_lognll, &m->view.gmm_lognll);
+    const float *bt_hi = nullptr, *bt_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
+    rc |= upload(m, H.basisT_hi, &bt_hi);
+    rc |= upload(m, H.basisT_lo, &bt_lo);
+    rc |= upload(m, H.w_hi, &w_hi);
+    rc |= upload(m, H.w_lo, &w_lo);
+    if (!rc) {
+        memset(&m->tc_maps, 0, sizeof(m->tc_maps));
+        m->tc_ok = tc_make_constant_maps(&m->tc_maps, bt_hi, bt_lo, w_hi, w_lo);
+        const char* no_tc = getenv("SMPLB200_DISABLE_TCGEN05");      // A/B switch for tests and benchmarks
+        if (no_tc && no_tc[0] == '1') m->tc_ok = false;
+    }
     if (rc) {
         smplb200_model_destroy(m);
         return 1;
@@ -116,14 +131,35 @@ extern "C" void smplb200_model_destroy(smplb200_model* m) {
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-extern "C" size_t smplb200_fit_workspace_bytes(int batch) {
-    if (batch < 0) return 0;
-    return align256((size_t)batch * 288 * 4) + align256((size_t)batch * kXPad * 4) + 256;
+// Device workspace: A [B][288], x [B][224] (CUDA-core vertex kernels), their hi/lo tf32 splits in the layouts
+// the tcgen05 kernel's TMA maps expect, and (SMPL backward only) the per-split partial sums.
+struct Work {
+    float *A, *x, *dA, *dx;
+    TcOperands tc;
+};
+static size_t work_bytes(int batch, bool with_backward) {
+    const size_t a = align256((size_t)batch * 288 * 4), x = align256((size_t)batch * kXPad * 4),
+                 ae = align256((size_t)batch * 12 * 32 * 4);
+    return a + x + 2 * x + 2 * ae + (with_backward ? (size_t)kMaxSplit * (a + x) : 0) + 256;
 }
-extern "C" size_t smplb200_smpl_workspace_bytes(int batch) {
-    if (batch < 0) return 0;
-    return (size_t)(1 + kMaxSplit) * (align256((size_t)batch * 288 * 4) + align256((size_t)batch * kXPad * 4)) + 256;
+static Work carve(void* ws, int batch) {
+    char* w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(ws)));
+    const size_t a = align256((size_t)batch * 288 * 4), x = align256((size_t)batch * kXPad * 4),
+                 ae = align256((size_t)batch * 12 * 32 * 4);
+    Work k;
+    k.A = reinterpret_cast<float*>(w); w += a;
+    k.x = reinterpret_cast<float*>(w); w += x;
+    k.tc.x_hi = reinterpret_cast<float*>(w); w += x;
+    k.tc.x_lo = reinterpret_cast<float*>(w); w += x;
+    k.tc.ae_hi = reinterpret_cast<float*>(w); w += ae;
+    k.tc.ae_lo = reinterpret_cast<float*>(w); w += ae;
+    k.dA = reinterpret_cast<float*>(w); w += (size_t)kMaxSplit * a;
+    k.dx = reinterpret_cast<float*>(w);
+    return k;
 }
+
+extern "C" size_t smplb200_fit_workspace_bytes(int batch) { return batch < 0 ? 0 : work_bytes(batch, false); }
+extern "C" size_t smplb200_smpl_workspace_bytes(int batch) { return batch < 0 ? 0 : work_bytes(batch, true); }
 
 static AdamConsts adam_consts(double beta1, double beta2) {
     AdamConsts c;
@@ -145,10 +181,8 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     if (num_iters < 0 || num_iters > kMaxIters) return fail("num_iters must be in [0, %d]", kMaxIters);
     if (!pose || !betas || !cam || !center || !kp || !reproj) return fail("smplify: NULL required buffer");
     if (ws_bytes < smplb200_fit_workspace_bytes(batch) || !ws) return fail("smplify: workspace too small");
-    char* w = static_cast<char*>(ws);
-    w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(w)));
-    float* ws_A = reinterpret_cast<float*>(w);
-    float* ws_x = reinterpret_cast<float*>(w + align256((size_t)batch * 288 * 4));
+    const Work wk = carve(ws, batch);
+    const bool use_tc = vertices && m->tc_ok;
     FitParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch;
@@ -157,15 +191,18 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     P.focal = focal;
     P.init_pose = pose; P.init_betas = betas; P.init_cam = cam; P.center = center; P.keypoints = kp;
     P.out_joints = joints; P.out_pose = opose; P.out_betas = obetas; P.out_cam = ocam; P.out_reproj = reproj;
-    P.ws_A = vertices ? ws_A : nullptr;
-    P.ws_x = vertices ? ws_x : nullptr;
+    if (use_tc) P.tc = wk.tc;
+    else if (vertices) { P.ws_A = wk.A; P.ws_x = wk.x; }
     P.loss_trace = trace;
     P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
     P.adam_c = adam_consts(P.beta1, P.beta2);
     CUDA_OK(launch_fit(m->view, P, st));
     ++g_launches;
-    if (vertices) {
-        CUDA_OK(launch_vertex_forward(m->view, ws_x, ws_A, vertices, nullptr, batch, st));
+    if (use_tc) {
+        CUDA_OK(launch_vertex_forward_tc(m->tc_maps, wk.tc, vertices, nullptr, batch, st));
+        ++g_launches;
+    } else if (vertices) {
+        CUDA_OK(launch_vertex_forward(m->view, wk.x, wk.A, vertices, nullptr, batch, st));
         ++g_launches;
     }
     return 0;
@@ -191,15 +228,6 @@ extern "C" int smplb200_smplify_fitting_loss(const smplb200_model* model, int ba
                    static_cast<cudaStream_t>(stream));
 }
 
-static void split_workspace(void* ws, int batch, float** A, float** x, float** dA, float** dx) {
-    char* w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(ws)));
-    const size_t a = align256((size_t)batch * 288 * 4), b = align256((size_t)batch * kXPad * 4);
-    *A = reinterpret_cast<float*>(w);
-    *x = reinterpret_cast<float*>(w + a);
-    *dA = reinterpret_cast<float*>(w + a + b);
-    *dx = reinterpret_cast<float*>(w + a + b + (size_t)kMaxSplit * a);
-}
-
 extern "C" int smplb200_smpl_forward(const smplb200_model* m, int batch, int rotmat_mode, const float* pose, const float* betas,
                                      float* vertices, float* joints, float* saved_vposed, void* workspace, size_t workspace_bytes,
                                      void* stream) {
@@ -209,16 +237,20 @@ extern "C" int smplb200_smpl_forward(const smplb200_model* m, int batch, int rot
     if (!pose || !betas) return fail("smpl_forward: NULL input");
     if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_forward: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float *A, *x, *dA, *dx;
-    split_workspace(workspace, batch, &A, &x, &dA, &dx);
+    const Work wk = carve(workspace, batch);
+    const bool use_tc = vertices && m->tc_ok;
     PoseParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas; P.joints = joints;
-    P.ws_A = A; P.ws_x = x;
+    if (use_tc) P.tc = wk.tc;
+    else if (vertices) { P.ws_A = wk.A; P.ws_x = wk.x; }
     CUDA_OK(launch_pose_forward(m->view, P, st));
     ++g_launches;
-    if (vertices) {
-        CUDA_OK(launch_vertex_forward(m->view, x, A, vertices, saved_vposed, batch, st));
+    if (use_tc) {
+        CUDA_OK(launch_vertex_forward_tc(m->tc_maps, wk.tc, vertices, saved_vposed, batch, st));
+        ++g_launches;
+    } else if (vertices) {
+        CUDA_OK(launch_vertex_forward(m->view, wk.x, wk.A, vertices, saved_vposed, batch, st));
         ++g_launches;
     }
     return 0;
@@ -234,8 +266,8 @@ extern "C" int smplb200_smpl_backward(const smplb200_model* m, int batch, int ro
     if (grad_vertices && !saved_vposed) return fail("smpl_backward: grad_vertices needs saved_vposed from the forward call");
     if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_backward: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float *A, *x, *dA, *dx;
-    split_workspace(workspace, batch, &A, &x, &dA, &dx);
+    const Work wk = carve(workspace, batch);
+    float *A = wk.A, *dA = wk.dA, *dx = wk.dx;
     PoseParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas;
@@ -339,7 +371,7 @@ extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, in
     CUDA_OK(cudaMemcpyAsync(d_cen, camera_center, B * 2 * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_kp, keypoints_2d, B * 147 * 4, cudaMemcpyHostToDevice, st));
     if (run_fit(m, batch, num_iters, step_size, focal_length, 0, d_pose, d_betas, d_cam, d_cen, d_kp, d_verts, o_joints, o_pose,
-                o_betas, o_cam, o_reproj, nullptr, ws, smplb200_fit_workspace_bytes(batch) + 512, st))
+                o_betas, o_cam, o_reproj, nullptr, ws, smplb200_fit_workspace_bytes(batch), st))
         return 1;
     CUDA_OK(cudaMemcpyAsync(joints, o_joints, B * 147 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(pose, o_pose, B * 72 * 4, cudaMemcpyDeviceToHost, st));

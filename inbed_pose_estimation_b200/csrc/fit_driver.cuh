@@ -5,6 +5,7 @@
 // They are __host__ __device__ so the TEST-ONLY emulation build can run them on the host.
 #pragma once
 #include "fit_tile.cuh"
+#include "lbs_tc.h"
 
 namespace smplb200 {
 
@@ -25,6 +26,7 @@ struct FitParams {
     float* out_reproj;        // [B][49]
     float* ws_A;              // [B][24][12] (nullable) skinning transforms of the final pose for the vertex kernel
     float* ws_x;              // [B][224]    (nullable) blend coefficients of the final pose
+    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernel
     float* loss_trace;        // [2*num_iters][B] (nullable) per-sample loss of every iteration
     double lr, beta1, beta2;  // Adam hyper-parameters (smplify.py:79,107: lr=step_size, betas=(0.9, 0.999))
     AdamConsts adam_c;
@@ -70,6 +72,43 @@ SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, boo
     TILE_SYNC();
     ph_output_joints<S>(M, C, sm);
     TILE_SYNC();
+}
+
+// Skinning transforms A = [G^R | A^t] and blend coefficients x of the tile's current pose, for the vertex
+// kernels: plain fp32 copies (CUDA-core kernels) and/or the hi/lo tf32 split operands of the tcgen05 kernel.
+template <int S>
+SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, float* ws_A, float* ws_x, const TcOperands& tc) {
+    using L = TileLayout<S>;
+    FOR_ITEMS(it, S * kXPad) {
+        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+        if (b >= batch) continue;
+        const float x = sm[L::XT + k * S + s];
+        if (ws_x) ws_x[(size_t)b * kXPad + k] = x;
+        if (tc.x_hi) {
+            const float hi = tf32_round(x);
+            tc.x_hi[(size_t)b * kXPad + k] = hi;
+            tc.x_lo[(size_t)b * kXPad + k] = x - hi;
+        }
+    }
+    if (ws_A) {
+        FOR_ITEMS(it, S * 288) {
+            const int s = it / 288, k = it % 288, b = tile * S + s;
+            const int j = k / 12, e = k % 12;
+            if (b < batch) ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
+        }
+    }
+    if (tc.ae_hi) {
+        FOR_ITEMS(it, S * 12 * 32) {
+            const int s = it / 384, r = it % 384, e = r / 32, j = r % 32, b = tile * S + s;
+            if (b >= batch) continue;
+            float a = 0.f;
+            if (j < kJoints) a = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + (j * 12 + e) * S + s];
+            const float hi = tf32_round(a);
+            const size_t o = ((size_t)e * batch + b) * 32 + j;
+            tc.ae_hi[o] = hi;
+            tc.ae_lo[o] = a - hi;
+        }
+    }
 }
 
 // Stage 1 (camera_fitting_loss, smplify.py:70-91): only the root rotation and the camera move, so all
@@ -261,16 +300,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    FOR_ITEMS(it, S * kXPad) {
-        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
-        if (P.ws_x && b < P.batch) P.ws_x[(size_t)b * kXPad + k] = sm[L::XT + k * S + s];
-    }
-    FOR_ITEMS(it, S * 288) {
-        const int s = it / 288, k = it % 288, b = tile * S + s;
-        const int j = k / 12, e = k % 12;
-        if (P.ws_A && b < P.batch)
-            P.ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
-    }
+    tile_write_vertex_operands<S>(sm, tile, P.batch, P.ws_A, P.ws_x, P.tc);
     TILE_SYNC();
     ph_reprojection<S>(sm, P.focal, kSigma2, false);
     TILE_SYNC();
@@ -303,6 +333,7 @@ struct PoseParams {
     float* joints;            // [B][49][3]
     float* ws_A;              // [B][24][12]
     float* ws_x;              // [B][224]
+    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernel
     // backward only
     const float* d_joints;    // [B][49][3] (nullable)
     const float* dA_part;     // [nsplit][B][288] (nullable) from the vertex backward kernel
@@ -343,16 +374,7 @@ SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, 
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    FOR_ITEMS(it, S * kXPad) {
-        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
-        if (P.ws_x && b < P.batch) P.ws_x[(size_t)b * kXPad + k] = sm[L::XT + k * S + s];
-    }
-    FOR_ITEMS(it, S * 288) {
-        const int s = it / 288, k = it % 288, b = tile * S + s;
-        const int j = k / 12, e = k % 12;
-        if (P.ws_A && b < P.batch)
-            P.ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
-    }
+    tile_write_vertex_operands<S>(sm, tile, P.batch, P.ws_A, P.ws_x, P.tc);
 }
 
 template <int S>

@@ -9,6 +9,7 @@
 // so that every joint the loss needs is an exact algebraic function of x = [1, beta, pose_feature]
 // and the 24 skinning transforms, without touching the 6890 vertices inside the fit loop.
 #include "model_host.h"
+#include "lbs_tc.h"
 
 #include <math.h>
 #include <string.h>
@@ -117,6 +118,23 @@ std::string build_host_model(const smplb200_model_desc& d, HostModel& H) {
         for (int n = 0; n < kCols; ++n) H.basisT[(size_t)n * kXPad + m] = H.basis[(size_t)m * kColsPad + n];
     H.weights.assign((size_t)(kVerts + 64) * kJoints, 0.f);
     memcpy(H.weights.data(), d.weights, sizeof(float) * (size_t)kVerts * kJoints);
+
+    // ---- tf32 hi/lo split of the tensor-core operands (3xTF32) ------------------------------------------
+    H.basisT_hi.assign(H.basisT.size(), 0.f);
+    H.basisT_lo.assign(H.basisT.size(), 0.f);
+    for (size_t i = 0; i < H.basisT.size(); ++i) {
+        const float hi = tf32_round(H.basisT[i]);
+        H.basisT_hi[i] = hi;
+        H.basisT_lo[i] = H.basisT[i] - hi;
+    }
+    H.w_hi.assign((size_t)kTcVertRowsPad * 32, 0.f);
+    H.w_lo.assign((size_t)kTcVertRowsPad * 32, 0.f);
+    for (int v = 0; v < kVerts; ++v)
+        for (int j = 0; j < kJoints; ++j) {
+            const float w = d.weights[(size_t)v * kJoints + j], hi = tf32_round(w);
+            H.w_hi[(size_t)v * 32 + j] = hi;
+            H.w_lo[(size_t)v * 32 + j] = w - hi;
+        }
 
     // ---- rest joints: J0 + JS.beta ------------------------------------------------------------------
     H.J0.assign(72, 0.f);
