@@ -17,7 +17,7 @@ from . import constants as C
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
-LIB_PATH = os.path.join(_HERE, 'libsmplify_b200.so')
+LIB_PATH = os.environ.get('SMPLB200_LIB') or os.path.join(_HERE, 'libsmplify_b200.so')   # override: profiling builds only
 SOURCES = ['kernels.cu', 'lbs_tc.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -42,22 +42,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile the CUDA library for sm_100a into the package directory."""
-    if not force and not _stale():
+    out = out or LIB_PATH
+    if out == LIB_PATH and not force and not _stale():
         return LIB_PATH
     nvcc = _nvcc()
     if nvcc is None:
         raise RuntimeError('nvcc not found: cannot build %s' % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', LIB_PATH + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-o', out + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout)
-    os.replace(LIB_PATH + '.tmp', LIB_PATH)
+    os.replace(out + '.tmp', out)
     if verbose:
         print(res.stdout)
-    return LIB_PATH
+    return out
 
 
 _f32p = ctypes.POINTER(ctypes.c_float)

@@ -51,6 +51,14 @@ static int fail(const char* fmt, ...) {
 
 extern "C" int smplb200_version(void) { return 100; }
 extern "C" const char* smplb200_last_error(void) { return g_error.c_str(); }
+#if defined(SMPLB200_PHASE_CLOCKS)
+// profiling builds only (tools/phase_clocks.py): read / reset the stage-2 phase cycle counters
+namespace smplb200 { cudaError_t debug_phase_clocks(unsigned long long* out32, int reset); }
+extern "C" int smplb200_debug_phase_clocks(unsigned long long* out32, int reset) {
+    return smplb200::debug_phase_clocks(out32, reset) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" long long smplb200_launch_count(int reset) {
     const long long v = g_launches;
     if (reset) g_launches = 0;

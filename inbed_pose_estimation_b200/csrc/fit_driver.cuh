@@ -9,6 +9,19 @@
 
 namespace smplb200 {
 
+// Optional per-phase cycle counters of the stage-2 loop (profiling builds only: -DSMPLB200_PHASE_CLOCKS;
+// tools/phase_clocks.py).  Thread 0 of CTA 0 accumulates the clock64() deltas between phase marks.
+#if defined(SMPLB200_PHASE_CLOCKS) && defined(__CUDACC__)
+static __device__ unsigned long long g_phase_clocks[32];      // one copy per translation unit; kernels.cu owns the live one
+#endif
+#if defined(SMPLB200_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define PHASE_BEGIN() long long ph_t0 = clock64(); const bool ph_on = (threadIdx.x == 0 && blockIdx.x == 0)
+#define PHASE_MARK(i) do { if (ph_on) { const long long t = clock64(); g_phase_clocks[i] += (unsigned long long)(t - ph_t0); ph_t0 = t; } } while (0)
+#else
+#define PHASE_BEGIN() ((void)0)
+#define PHASE_MARK(i) ((void)0)
+#endif
+
 struct FitParams {
     int batch;
     int num_iters;            // per stage; 0 => only the final forward (get_fitting_loss)
@@ -242,12 +255,26 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
         TILE_SYNC();
 
         // ---- stage 2: body pose, betas, global orientation (body_fitting_loss) ----------------
+        PHASE_BEGIN();
         for (int it = 0; it < P.num_iters; ++it) {
             ph_prior_quadratic<S>(M, C, sm);
             TILE_SYNC();
+            PHASE_MARK(0);
             ph_prior_select<S>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
             TILE_SYNC();
-            tile_forward<S>(M, C, sm, true, false);
+            PHASE_MARK(1);
+            ph_pose_features<S>(sm, true, false);
+            ph_rest_joints<S>(C, sm);
+            TILE_SYNC();
+            PHASE_MARK(2);
+            ph_chain_forward<S>(M, sm);           // ends with a barrier
+            PHASE_MARK(3);
+            ph_fold_gemm_forward<S>(M, sm);
+            TILE_SYNC();
+            PHASE_MARK(4);
+            ph_output_joints<S>(M, C, sm);
+            TILE_SYNC();
+            PHASE_MARK(5);
             ph_reprojection<S>(sm, P.focal, kSigma2, true);
             zero_rows<S>(sm, L::DG, 288);
             TILE_SYNC();
@@ -260,14 +287,19 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
                     if (b < P.batch) P.loss_trace[(size_t)(P.num_iters + it) * P.batch + b] = a;
                 }
             }
+            PHASE_MARK(6);
             ph_joint_backward<S>(M, C, sm);
             TILE_SYNC();
+            PHASE_MARK(7);
             ph_pick_backward<S>(M, C, sm);
             TILE_SYNC();
+            PHASE_MARK(8);
             ph_fold_gemm_backward<S>(M, sm);
             TILE_SYNC();
+            PHASE_MARK(9);
             ph_chain_backward<S>(M, sm);
             TILE_SYNC();
+            PHASE_MARK(10);
             const AdamScalars sc = adam_tab[it];
             FOR_ITEMS(itj, kJoints * S) {
                 const int s = itj % S, j = itj / S;
@@ -291,6 +323,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
                                                       P.adam_c, sc);
             }
             TILE_SYNC();
+            PHASE_MARK(11);
         }
     }
 

@@ -9,6 +9,7 @@
 //   projection_{fwd,bwd}         utils/geometry.py:79-107
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "fit_driver.cuh"
 #include "launch.h"
 
@@ -17,9 +18,9 @@ namespace smplb200 {
 // ------------------------------------------------------------------------------------------------
 // tile kernels
 // ------------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(kFitThreads, 1) smplify_fit_kernel(const __grid_constant__ ModelView M,
-                                                                     const __grid_constant__ FitParams P) {
+template <int S, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) smplify_fit_kernel(const __grid_constant__ ModelView M,
+                                                               const __grid_constant__ FitParams P) {
     extern __shared__ __align__(16) float sm[];
     fit_tile<S>(M, P, blockIdx.x, sm);
 }
@@ -46,26 +47,36 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+#if defined(SMPLB200_PHASE_CLOCKS)
+cudaError_t debug_phase_clocks(unsigned long long* out32, int reset) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && out32) e = cudaMemcpyFromSymbol(out32, g_phase_clocks, sizeof(unsigned long long) * 32);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[32] = {0};
+        e = cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z));
+    }
+    return e;
+}
+#endif
+
+template <int S, int NT, int MINB>
+static cudaError_t launch_fit_variant(const ModelView& M, const FitParams& P, cudaStream_t stream) {
+    cudaError_t e = opt_in_smem(smplify_fit_kernel<S, NT, MINB>, tile_smem_bytes<S>());
+    if (e != cudaSuccess) return e;
+    smplify_fit_kernel<S, NT, MINB><<<(P.batch + S - 1) / S, NT, tile_smem_bytes<S>(), stream>>>(M, P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream) {
     if (P.batch <= 0) return cudaSuccess;
+    static const int variant = [] { const char* v = getenv("SMPLB200_FIT_VARIANT"); return v ? atoi(v) : 0; }();
+    if (variant == 1) return launch_fit_variant<8, 192, 2>(M, P, stream);
+    if (variant == 2) return launch_fit_variant<8, 256, 2>(M, P, stream);
+    if (variant == 3) return launch_fit_variant<16, 384, 1>(M, P, stream);
     // Large batches: 16 samples per CTA amortise the streamed folded basis; small ones: spread over more SMs.
-    if (P.batch >= 16 * 64) {
-        constexpr int S = 16;
-        cudaError_t e = opt_in_smem(smplify_fit_kernel<S>, tile_smem_bytes<S>());
-        if (e != cudaSuccess) return e;
-        smplify_fit_kernel<S><<<(P.batch + S - 1) / S, kFitThreads, tile_smem_bytes<S>(), stream>>>(M, P);
-    } else if (P.batch >= 8 * 64) {
-        constexpr int S = 8;
-        cudaError_t e = opt_in_smem(smplify_fit_kernel<S>, tile_smem_bytes<S>());
-        if (e != cudaSuccess) return e;
-        smplify_fit_kernel<S><<<(P.batch + S - 1) / S, kFitThreads, tile_smem_bytes<S>(), stream>>>(M, P);
-    } else {
-        constexpr int S = 4;
-        cudaError_t e = opt_in_smem(smplify_fit_kernel<S>, tile_smem_bytes<S>());
-        if (e != cudaSuccess) return e;
-        smplify_fit_kernel<S><<<(P.batch + S - 1) / S, kFitThreads, tile_smem_bytes<S>(), stream>>>(M, P);
-    }
-    return cudaGetLastError();
+    if (P.batch >= 16 * 64) return launch_fit_variant<16, kFitThreads, 1>(M, P, stream);
+    if (P.batch >= 8 * 64) return launch_fit_variant<8, kFitThreads, 1>(M, P, stream);
+    return launch_fit_variant<4, kFitThreads, 1>(M, P, stream);
 }
 
 cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
