@@ -22,6 +22,8 @@ SOURCES = ['kernels.cu', 'lbs_tc.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
+VPOSED_PITCH = 20736     # SMPLB200_VPOSED_PITCH: floats per row of the saved v_posed buffer
+
 _lock = threading.Lock()
 _lib = None
 

@@ -21,8 +21,7 @@ struct smplb200_model {
     int device = 0;
     ModelView view;
     bool has_prior = false;
-    bool tc_ok = false;            // tcgen05 vertex kernel usable (tensor maps encoded)
-    TcMaps tc_maps;
+    TcConstMaps tc_maps;           // TMA maps of the tcgen05 vertex kernels' constant operands
     std::vector<void*> allocations;
     // grow-only device scratch + pinned staging of the host-buffer entry point
     std::mutex mu;
@@ -96,9 +95,6 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
     m->view = H.view;
     m->has_prior = H.has_prior;
     int rc = 0;
-    rc |= upload(m, H.basis, &m->view.basis);
-    rc |= upload(m, H.basisT, &m->view.basisT);
-    rc |= upload(m, H.weights, &m->view.weights);
     rc |= upload(m, H.Cf, &m->view.Cf);
     rc |= upload(m, H.CfT, &m->view.CfT);
     rc |= upload(m, H.wkj, &m->view.wkj);
@@ -109,16 +105,20 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
     rc |= upload(m, H.gmm_prec, &m->view.gmm_prec);
     rc |= upload(m, H.gmm_pmean, &m->view.gmm_pmean);
     rc |= upload(m, H.gmm_lognll, &m->view.gmm_lognll);
-    const float *bt_hi = nullptr, *bt_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
+    const float *bt_hi = nullptr, *bt_lo = nullptr, *bm_hi = nullptr, *bm_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr,
+                *wT_hi = nullptr, *wT_lo = nullptr;
     rc |= upload(m, H.basisT_hi, &bt_hi);
     rc |= upload(m, H.basisT_lo, &bt_lo);
+    rc |= upload(m, H.basis_hi, &bm_hi);
+    rc |= upload(m, H.basis_lo, &bm_lo);
     rc |= upload(m, H.w_hi, &w_hi);
     rc |= upload(m, H.w_lo, &w_lo);
+    rc |= upload(m, H.wT_hi, &wT_hi);
+    rc |= upload(m, H.wT_lo, &wT_lo);
     if (!rc) {
         memset(&m->tc_maps, 0, sizeof(m->tc_maps));
-        m->tc_ok = tc_make_constant_maps(&m->tc_maps, bt_hi, bt_lo, w_hi, w_lo);
-        const char* no_tc = getenv("SMPLB200_DISABLE_TCGEN05");      // A/B switch for tests and benchmarks
-        if (no_tc && no_tc[0] == '1') m->tc_ok = false;
+        if (!tc_make_constant_maps(&m->tc_maps, bt_hi, bt_lo, bm_hi, bm_lo, w_hi, w_lo, wT_hi, wT_lo))
+            rc = fail("smplb200_model_create: cuTensorMapEncodeTiled failed (TMA descriptors of the tcgen05 kernels)");
     }
     if (rc) {
         smplb200_model_destroy(m);
@@ -139,35 +139,46 @@ extern "C" void smplb200_model_destroy(smplb200_model* m) {
 
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// Device workspace: A [B][288], x [B][224] (CUDA-core vertex kernels), their hi/lo tf32 splits in the layouts
-// the tcgen05 kernel's TMA maps expect, and (SMPL backward only) the per-split partial sums.
+// Device workspace.  The pose kernels write the per-sample operands of the tcgen05 vertex kernels (x hi/lo [B][224],
+// skinning transforms hi/lo [B][12][32]); `big0` holds v_posed [B][20736] in forward calls without a caller-supplied
+// saved buffer and dvp_hi in backward calls, `big1` dvp_lo (backward only), then the per-split partial sums.
 struct Work {
-    float *A, *x, *dA, *dx;
     TcOperands tc;
+    float *big0, *big1, *dA, *dx;
 };
+static size_t big_bytes(int batch) { return align256((size_t)batch * kVpPitch * 4); }
 static size_t work_bytes(int batch, bool with_backward) {
-    const size_t a = align256((size_t)batch * 288 * 4), x = align256((size_t)batch * kXPad * 4),
-                 ae = align256((size_t)batch * 12 * 32 * 4);
-    return a + x + 2 * x + 2 * ae + (with_backward ? (size_t)kMaxSplit * (a + x) : 0) + 256;
+    const size_t x = align256((size_t)batch * kXPad * 4), ae = align256((size_t)batch * kAeRow * 4);
+    size_t n = 2 * x + 2 * ae + big_bytes(batch) + 256;
+    if (with_backward)
+        n += big_bytes(batch) + (size_t)kMaxSplitA * align256((size_t)batch * 288 * 4) + (size_t)kMaxSplitX * x;
+    return n;
 }
 static Work carve(void* ws, int batch) {
     char* w = reinterpret_cast<char*>(align256(reinterpret_cast<size_t>(ws)));
-    const size_t a = align256((size_t)batch * 288 * 4), x = align256((size_t)batch * kXPad * 4),
-                 ae = align256((size_t)batch * 12 * 32 * 4);
+    const size_t x = align256((size_t)batch * kXPad * 4), ae = align256((size_t)batch * kAeRow * 4);
     Work k;
-    k.A = reinterpret_cast<float*>(w); w += a;
-    k.x = reinterpret_cast<float*>(w); w += x;
     k.tc.x_hi = reinterpret_cast<float*>(w); w += x;
     k.tc.x_lo = reinterpret_cast<float*>(w); w += x;
     k.tc.ae_hi = reinterpret_cast<float*>(w); w += ae;
     k.tc.ae_lo = reinterpret_cast<float*>(w); w += ae;
-    k.dA = reinterpret_cast<float*>(w); w += (size_t)kMaxSplit * a;
+    k.big0 = reinterpret_cast<float*>(w); w += big_bytes(batch);
+    k.big1 = reinterpret_cast<float*>(w); w += big_bytes(batch);          // backward workspaces only
+    k.dA = reinterpret_cast<float*>(w); w += (size_t)kMaxSplitA * align256((size_t)batch * 288 * 4);
     k.dx = reinterpret_cast<float*>(w);
     return k;
 }
 
 extern "C" size_t smplb200_fit_workspace_bytes(int batch) { return batch < 0 ? 0 : work_bytes(batch, false); }
 extern "C" size_t smplb200_smpl_workspace_bytes(int batch) { return batch < 0 ? 0 : work_bytes(batch, true); }
+
+// blend-shape GEMM + skinning of all 6890 vertices from the operands the pose / fit kernel left in the workspace
+static int run_vertices(const smplb200_model* m, const Work& wk, float* vposed, float* vertices, int batch, cudaStream_t st) {
+    CUDA_OK(launch_blend_gemm(m->tc_maps, wk.tc.x_hi, wk.tc.x_lo, vposed, batch, st));
+    CUDA_OK(launch_skin_forward(m->tc_maps, wk.tc.ae_hi, wk.tc.ae_lo, vposed, vertices, batch, st));
+    g_launches += 2;
+    return 0;
+}
 
 static AdamConsts adam_consts(double beta1, double beta2) {
     AdamConsts c;
@@ -190,7 +201,6 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     if (!pose || !betas || !cam || !center || !kp || !reproj) return fail("smplify: NULL required buffer");
     if (ws_bytes < smplb200_fit_workspace_bytes(batch) || !ws) return fail("smplify: workspace too small");
     const Work wk = carve(ws, batch);
-    const bool use_tc = vertices && m->tc_ok;
     FitParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch;
@@ -199,20 +209,13 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     P.focal = focal;
     P.init_pose = pose; P.init_betas = betas; P.init_cam = cam; P.center = center; P.keypoints = kp;
     P.out_joints = joints; P.out_pose = opose; P.out_betas = obetas; P.out_cam = ocam; P.out_reproj = reproj;
-    if (use_tc) P.tc = wk.tc;
-    else if (vertices) { P.ws_A = wk.A; P.ws_x = wk.x; }
+    if (vertices) P.tc = wk.tc;
     P.loss_trace = trace;
     P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
     P.adam_c = adam_consts(P.beta1, P.beta2);
     CUDA_OK(launch_fit(m->view, P, st));
     ++g_launches;
-    if (use_tc) {
-        CUDA_OK(launch_vertex_forward_tc(m->tc_maps, wk.tc, vertices, nullptr, batch, st));
-        ++g_launches;
-    } else if (vertices) {
-        CUDA_OK(launch_vertex_forward(m->view, wk.x, wk.A, vertices, nullptr, batch, st));
-        ++g_launches;
-    }
+    if (vertices && run_vertices(m, wk, wk.big0, vertices, batch, st)) return 1;
     return 0;
 }
 
@@ -246,21 +249,13 @@ extern "C" int smplb200_smpl_forward(const smplb200_model* m, int batch, int rot
     if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_forward: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Work wk = carve(workspace, batch);
-    const bool use_tc = vertices && m->tc_ok;
     PoseParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas; P.joints = joints;
-    if (use_tc) P.tc = wk.tc;
-    else if (vertices) { P.ws_A = wk.A; P.ws_x = wk.x; }
+    if (vertices) P.tc = wk.tc;
     CUDA_OK(launch_pose_forward(m->view, P, st));
     ++g_launches;
-    if (use_tc) {
-        CUDA_OK(launch_vertex_forward_tc(m->tc_maps, wk.tc, vertices, saved_vposed, batch, st));
-        ++g_launches;
-    } else if (vertices) {
-        CUDA_OK(launch_vertex_forward(m->view, wk.x, wk.A, vertices, saved_vposed, batch, st));
-        ++g_launches;
-    }
+    if (vertices && run_vertices(m, wk, saved_vposed ? saved_vposed : wk.big0, vertices, batch, st)) return 1;
     return 0;
 }
 
@@ -275,24 +270,21 @@ extern "C" int smplb200_smpl_backward(const smplb200_model* m, int batch, int ro
     if (!workspace || workspace_bytes < smplb200_smpl_workspace_bytes(batch)) return fail("smpl_backward: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Work wk = carve(workspace, batch);
-    float *A = wk.A, *dA = wk.dA, *dx = wk.dx;
     PoseParams P;
     memset(&P, 0, sizeof(P));
     P.batch = batch; P.rotmat_mode = rotmat_mode; P.pose = pose; P.betas = betas;
-    int nsplit = 0;
     if (grad_vertices) {
-        // A of the forward pass is recomputed (cheap) so that the backward call is self-contained.
+        // The skinning transforms of the forward pass are recomputed (cheap) so that the backward call is self-contained.
         PoseParams F = P;
-        F.ws_A = A;
+        F.tc = wk.tc;
+        F.tc.x_hi = nullptr; F.tc.x_lo = nullptr;
         CUDA_OK(launch_pose_forward(m->view, F, st));
-        ++g_launches;
-        const int tiles = (batch + 15) / 16;
-        nsplit = (2 * 148 + tiles - 1) / tiles;
-        if (nsplit < 1) nsplit = 1;
-        if (nsplit > kMaxSplit) nsplit = kMaxSplit;
-        CUDA_OK(launch_vertex_backward(m->view, A, saved_vposed, grad_vertices, dA, dx, batch, nsplit, st));
-        ++g_launches;
-        P.dA_part = dA; P.dx_part = dx; P.nsplit = nsplit;
+        const int nsa = tc_dA_splits(batch), nsx = tc_dx_splits(batch);
+        CUDA_OK(launch_skin_backward(m->tc_maps, wk.tc.ae_hi, wk.tc.ae_lo, grad_vertices, wk.big0, wk.big1, batch, st));
+        CUDA_OK(launch_dx_gemm(m->tc_maps, wk.big0, wk.big1, wk.dx, batch, nsx, st));
+        CUDA_OK(launch_dA(m->tc_maps, grad_vertices, saved_vposed, wk.dA, batch, nsa, st));
+        g_launches += 4;
+        P.dA_part = wk.dA; P.dx_part = wk.dx; P.nsplit_a = nsa; P.nsplit_x = nsx;
     }
     P.d_joints = grad_joints; P.d_pose = grad_pose; P.d_betas = grad_betas;
     CUDA_OK(launch_pose_backward(m->view, P, st));

@@ -37,9 +37,7 @@ struct FitParams {
     float* out_betas;         // [B][10]     (nullable)
     float* out_cam;           // [B][3]      (nullable)
     float* out_reproj;        // [B][49]
-    float* ws_A;              // [B][24][12] (nullable) skinning transforms of the final pose for the vertex kernel
-    float* ws_x;              // [B][224]    (nullable) blend coefficients of the final pose
-    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernel
+    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernels for the final pose
     float* loss_trace;        // [2*num_iters][B] (nullable) per-sample loss of every iteration
     double lr, beta1, beta2;  // Adam hyper-parameters (smplify.py:79,107: lr=step_size, betas=(0.9, 0.999))
     AdamConsts adam_c;
@@ -87,37 +85,29 @@ SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, boo
     TILE_SYNC();
 }
 
-// Skinning transforms A = [G^R | A^t] and blend coefficients x of the tile's current pose, for the vertex
-// kernels: plain fp32 copies (CUDA-core kernels) and/or the hi/lo tf32 split operands of the tcgen05 kernel.
+// Skinning transforms A = [G^R | A^t] and blend coefficients x of the tile's current pose, written as the hi/lo tf32
+// split operands of the tcgen05 vertex kernels (lbs_tc.cu): x [B][224], transforms [B][12 entries][24 joints + 8 pad].
 template <int S>
-SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, float* ws_A, float* ws_x, const TcOperands& tc) {
+SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, const TcOperands& tc) {
     using L = TileLayout<S>;
-    FOR_ITEMS(it, S * kXPad) {
-        const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
-        if (b >= batch) continue;
-        const float x = sm[L::XT + k * S + s];
-        if (ws_x) ws_x[(size_t)b * kXPad + k] = x;
-        if (tc.x_hi) {
+    if (tc.x_hi) {
+        FOR_ITEMS(it, S * kXPad) {
+            const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+            if (b >= batch) continue;
+            const float x = sm[L::XT + k * S + s];
             const float hi = tf32_round(x);
             tc.x_hi[(size_t)b * kXPad + k] = hi;
             tc.x_lo[(size_t)b * kXPad + k] = x - hi;
         }
     }
-    if (ws_A) {
-        FOR_ITEMS(it, S * 288) {
-            const int s = it / 288, k = it % 288, b = tile * S + s;
-            const int j = k / 12, e = k % 12;
-            if (b < batch) ws_A[(size_t)b * 288 + k] = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + k * S + s];
-        }
-    }
     if (tc.ae_hi) {
-        FOR_ITEMS(it, S * 12 * 32) {
-            const int s = it / 384, r = it % 384, e = r / 32, j = r % 32, b = tile * S + s;
+        FOR_ITEMS(it, S * kAeRow) {
+            const int s = it / kAeRow, r = it % kAeRow, e = r / 32, j = r % 32, b = tile * S + s;
             if (b >= batch) continue;
             float a = 0.f;
             if (j < kJoints) a = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + (j * 12 + e) * S + s];
             const float hi = tf32_round(a);
-            const size_t o = ((size_t)e * batch + b) * 32 + j;
+            const size_t o = (size_t)b * kAeRow + r;
             tc.ae_hi[o] = hi;
             tc.ae_lo[o] = a - hi;
         }
@@ -333,7 +323,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, tile, P.batch, P.ws_A, P.ws_x, P.tc);
+    tile_write_vertex_operands<S>(sm, tile, P.batch, P.tc);
     TILE_SYNC();
     ph_reprojection<S>(sm, P.focal, kSigma2, false);
     TILE_SYNC();
@@ -364,14 +354,12 @@ struct PoseParams {
     const float* pose;
     const float* betas;       // [B][10]
     float* joints;            // [B][49][3]
-    float* ws_A;              // [B][24][12]
-    float* ws_x;              // [B][224]
-    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernel
+    TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernels
     // backward only
     const float* d_joints;    // [B][49][3] (nullable)
-    const float* dA_part;     // [nsplit][B][288] (nullable) from the vertex backward kernel
-    const float* dx_part;     // [nsplit][B][224] (nullable)
-    int nsplit;
+    const float* dA_part;     // [nsplit_a][B][12][24] (nullable) partial dL/dA of the dA kernel, entry-major
+    const float* dx_part;     // [nsplit_x][B][224]    (nullable) partial dL/dx of the dx GEMM
+    int nsplit_a, nsplit_x;
     float* d_pose;            // [B][72] or [B][24][9]
     float* d_betas;           // [B][10]
 };
@@ -407,7 +395,7 @@ SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, 
         const int s = it / 147, k = it % 147, b = tile * S + s;
         if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, tile, P.batch, P.ws_A, P.ws_x, P.tc);
+    tile_write_vertex_operands<S>(sm, tile, P.batch, P.tc);
 }
 
 template <int S>
@@ -423,8 +411,10 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
     FOR_ITEMS(it, S * 288) {
         const int s = it / 288, k = it % 288, b = tile * S + s;
         float a = 0.f;
-        if (P.dA_part && b < P.batch)
-            for (int sp = 0; sp < P.nsplit; ++sp) a += P.dA_part[((size_t)sp * P.batch + b) * 288 + k];
+        if (P.dA_part && b < P.batch) {
+            const int j = k / 12, e = k % 12;
+            for (int sp = 0; sp < P.nsplit_a; ++sp) a += P.dA_part[(((size_t)sp * P.batch + b) * 12 + e) * kJoints + j];
+        }
         sm[L::DG + k * S + s] = a;
     }
     TILE_SYNC();
@@ -439,7 +429,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
             const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
             if (b < P.batch) {
                 float a = sm[L::XT + k * S + s];
-                for (int sp = 0; sp < P.nsplit; ++sp) a += P.dx_part[((size_t)sp * P.batch + b) * kXPad + k];
+                for (int sp = 0; sp < P.nsplit_x; ++sp) a += P.dx_part[((size_t)sp * P.batch + b) * kXPad + k];
                 sm[L::XT + k * S + s] = a;
             }
         }

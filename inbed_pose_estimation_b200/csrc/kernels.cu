@@ -3,8 +3,7 @@
 //   smplify_fit_kernel<S>        one CTA = S samples, the whole two-stage fit in one launch
 //   pose_forward_kernel<S>       per-sample half of SMPL.forward (joints, skinning transforms, blend coefficients)
 //   pose_backward_kernel<S>      its gradient
-//   lbs_vertex_forward_kernel    blend shapes + skinning for all 6890 vertices   (smplx lbs, SURVEY §8a a6,a9,a11)
-//   lbs_vertex_backward_kernel   dL/dverts -> dL/dA, dL/dx partial sums
+//   (the per-vertex half - blend shapes, skinning and their gradients - is the tcgen05 path in lbs_tc.cu)
 //   quat_rodrigues_{fwd,bwd}     utils/geometry.py:9-45
 //   projection_{fwd,bwd}         utils/geometry.py:79-107
 #include <cuda_runtime.h>
@@ -94,226 +93,6 @@ cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaSt
     cudaError_t e = opt_in_smem(pose_backward_kernel<S>, tile_smem_bytes<S>());
     if (e != cudaSuccess) return e;
     pose_backward_kernel<S><<<(P.batch + S - 1) / S, kPoseThreads, tile_smem_bytes<S>(), stream>>>(M, P);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// vertex kernels (CUDA-core version): v_posed = x . basis ; verts = (W . A) [v_posed ; 1]
-// ------------------------------------------------------------------------------------------------
-constexpr int kTV = 64;      // vertices per CTA tile
-constexpr int kVTiles = (kVerts + kTV - 1) / kTV;   // 108
-
-template <int TB>
-__global__ void __launch_bounds__(256) lbs_vertex_forward_kernel(const __grid_constant__ ModelView M,
-                                                                 const float* __restrict__ x, const float* __restrict__ A,
-                                                                 float* __restrict__ verts, float* __restrict__ vposed, int batch) {
-    constexpr int SPT = TB / 4;
-    extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                 // [kX][TB]
-    float* As = sm + kX * TB;       // [TB][288]
-    const int tid = threadIdx.x, v0 = blockIdx.x * kTV, b0 = blockIdx.y * TB;
-    for (int it = tid; it < TB * kX; it += 256) {
-        const int s = it / kX, k = it % kX;
-        xs[k * TB + s] = (b0 + s < batch) ? x[(size_t)(b0 + s) * kXPad + k] : 0.f;
-    }
-    for (int it = tid; it < TB * 288; it += 256)
-        As[it] = (b0 + it / 288 < batch) ? A[(size_t)b0 * 288 + it] : 0.f;
-    __syncthreads();
-
-    const int vl = tid & (kTV - 1), sg = tid / kTV, v = v0 + vl;
-    const bool vok = v < kVerts;
-    float acc[SPT][3];
-#pragma unroll
-    for (int i = 0; i < SPT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
-    const float* bcol = M.basis + 3 * v;         // padded columns are zero, always in bounds
-#pragma unroll 2
-    for (int k = 0; k < kX; ++k) {
-        const float b0v = bcol[(size_t)k * kColsPad + 0], b1v = bcol[(size_t)k * kColsPad + 1], b2v = bcol[(size_t)k * kColsPad + 2];
-        const float4* xr = reinterpret_cast<const float4*>(xs + k * TB + sg * SPT);
-#pragma unroll
-        for (int q = 0; q < SPT / 4; ++q) {
-            const float4 xv = xr[q];
-            const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                acc[4 * q + u][0] += xx[u] * b0v; acc[4 * q + u][1] += xx[u] * b1v; acc[4 * q + u][2] += xx[u] * b2v;
-            }
-        }
-    }
-    float w[kJoints];
-    if (vok) {
-        const float4* wr = reinterpret_cast<const float4*>(M.weights + (size_t)v * kJoints);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) { const float4 t = wr[q]; w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kJoints; ++j) w[j] = 0.f;
-    }
-#pragma unroll 1
-    for (int i = 0; i < SPT; ++i) {
-        const int s = sg * SPT + i, b = b0 + s;
-        float T[12];
-#pragma unroll
-        for (int e = 0; e < 12; ++e) T[e] = 0.f;
-        const float4* Ar = reinterpret_cast<const float4*>(As + s * 288);
-#pragma unroll
-        for (int j = 0; j < kJoints; ++j) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float4 a = Ar[j * 3 + r];
-                T[r * 4 + 0] += w[j] * a.x; T[r * 4 + 1] += w[j] * a.y; T[r * 4 + 2] += w[j] * a.z; T[r * 4 + 3] += w[j] * a.w;
-            }
-        }
-        if (vok && b < batch) {
-            const float px = acc[i][0], py = acc[i][1], pz = acc[i][2];
-            float* o = verts + (size_t)b * kCols + 3 * v;
-            o[0] = T[0] * px + T[1] * py + T[2] * pz + T[3];
-            o[1] = T[4] * px + T[5] * py + T[6] * pz + T[7];
-            o[2] = T[8] * px + T[9] * py + T[10] * pz + T[11];
-            if (vposed) {
-                float* vp = vposed + (size_t)b * kCols + 3 * v;
-                vp[0] = px; vp[1] = py; vp[2] = pz;
-            }
-        }
-    }
-}
-
-cudaError_t launch_vertex_forward(const ModelView& M, const float* x, const float* A, float* verts, float* vposed,
-                                  int batch, cudaStream_t stream) {
-    if (batch <= 0) return cudaSuccess;
-    constexpr int TB = 32;
-    const size_t smem = (size_t)(kX * TB + TB * 288) * sizeof(float);
-    cudaError_t e = opt_in_smem(lbs_vertex_forward_kernel<TB>, smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(kVTiles, (batch + TB - 1) / TB);
-    lbs_vertex_forward_kernel<TB><<<grid, 256, smem, stream>>>(M, x, A, verts, vposed, batch);
-    return cudaGetLastError();
-}
-
-// Backward: per (sample, vertex)  T = W.A ; dvp = T^R^T dV ; dT = dV (x) [vp;1] ;
-//   dA[s][j][e] += W[v][j] dT[s][v][e]      (reduced over the CTA's vertex range)
-//   dx[s][m]    += basis[m][3v+c] dvp[s][v][c]
-// Each CTA owns TB samples and 1/nsplit of the vertex tiles; partial sums are written once
-// (deterministic, no atomics) and added up by pose_backward_kernel.
-constexpr int kBwdTB = 16;
-__global__ void __launch_bounds__(256) lbs_vertex_backward_kernel(const __grid_constant__ ModelView M,
-                                                                  const float* __restrict__ A, const float* __restrict__ vposed,
-                                                                  const float* __restrict__ dverts, float* __restrict__ dA_part,
-                                                                  float* __restrict__ dx_part, int batch, int nsplit) {
-    constexpr int TB = kBwdTB, SPT = TB / 4;
-    extern __shared__ __align__(16) float sm[];
-    float* As = sm;                          // [TB][288]
-    float* Ws = As + TB * 288;               // [kTV][24]
-    float* dTs = Ws + kTV * kJoints;         // [kTV][TB][12]
-    float* dvps = dTs + kTV * TB * 12;       // [3*kTV][TB]
-    const int tid = threadIdx.x, split = blockIdx.x, b0 = blockIdx.y * TB;
-    for (int it = tid; it < TB * 288; it += 256)
-        As[it] = (b0 + it / 288 < batch) ? A[(size_t)b0 * 288 + it] : 0.f;
-    float accA[kJoints], accX[TB];
-#pragma unroll
-    for (int j = 0; j < kJoints; ++j) accA[j] = 0.f;
-#pragma unroll
-    for (int s = 0; s < TB; ++s) accX[s] = 0.f;
-    const int vl = tid & (kTV - 1), sg = tid / kTV;
-    const int t0 = (kVTiles * split) / nsplit, t1 = (kVTiles * (split + 1)) / nsplit;
-    __syncthreads();
-    for (int vt = t0; vt < t1; ++vt) {
-        const int v = vt * kTV + vl;
-        const bool vok = v < kVerts;
-        float w[kJoints];
-        if (vok) {
-            const float4* wr = reinterpret_cast<const float4*>(M.weights + (size_t)v * kJoints);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { const float4 t = wr[q]; w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kJoints; ++j) w[j] = 0.f;
-        }
-        if (sg == 0) {
-#pragma unroll
-            for (int j = 0; j < kJoints; ++j) Ws[vl * kJoints + j] = w[j];
-        }
-#pragma unroll 1
-        for (int i = 0; i < SPT; ++i) {
-            const int s = sg * SPT + i, b = b0 + s;
-            float T[12];
-#pragma unroll
-            for (int e = 0; e < 12; ++e) T[e] = 0.f;
-            const float4* Ar = reinterpret_cast<const float4*>(As + s * 288);
-#pragma unroll
-            for (int j = 0; j < kJoints; ++j) {
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float4 a = Ar[j * 3 + r];
-                    T[r * 4 + 0] += w[j] * a.x; T[r * 4 + 1] += w[j] * a.y; T[r * 4 + 2] += w[j] * a.z; T[r * 4 + 3] += w[j] * a.w;
-                }
-            }
-            float dV[3] = {0.f, 0.f, 0.f}, vp[3] = {0.f, 0.f, 0.f};
-            if (vok && b < batch) {
-                const float* g = dverts + (size_t)b * kCols + 3 * v;
-                const float* p = vposed + (size_t)b * kCols + 3 * v;
-                dV[0] = g[0]; dV[1] = g[1]; dV[2] = g[2];
-                vp[0] = p[0]; vp[1] = p[1]; vp[2] = p[2];
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                dvps[(3 * vl + c) * TB + s] = T[0 + c] * dV[0] + T[4 + c] * dV[1] + T[8 + c] * dV[2];
-            float* dT = dTs + (vl * TB + s) * 12;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                dT[r * 4 + 0] = dV[r] * vp[0]; dT[r * 4 + 1] = dV[r] * vp[1]; dT[r * 4 + 2] = dV[r] * vp[2]; dT[r * 4 + 3] = dV[r];
-            }
-        }
-        __syncthreads();
-        if (tid < TB * 12) {                      // thread = (sample, entry of the 3x4), accumulates over joints
-            for (int vv = 0; vv < kTV; ++vv) {
-                const float d = dTs[vv * TB * 12 + tid];
-                const float4* wr = reinterpret_cast<const float4*>(Ws + vv * kJoints);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const float4 t = wr[q];
-                    accA[4 * q] += t.x * d; accA[4 * q + 1] += t.y * d; accA[4 * q + 2] += t.z * d; accA[4 * q + 3] += t.w * d;
-                }
-            }
-        }
-        if (tid < kXPad) {                        // thread = blend coefficient m, accumulates over the tile's columns
-            const float* bt = M.basisT + (size_t)(3 * vt * kTV) * kXPad + tid;
-#pragma unroll 2
-            for (int n = 0; n < 3 * kTV; ++n) {
-                const float c = bt[(size_t)n * kXPad];
-                const float4* dr = reinterpret_cast<const float4*>(dvps + n * TB);
-#pragma unroll
-                for (int q = 0; q < TB / 4; ++q) {
-                    const float4 d = dr[q];
-                    accX[4 * q] += c * d.x; accX[4 * q + 1] += c * d.y; accX[4 * q + 2] += c * d.z; accX[4 * q + 3] += c * d.w;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (tid < TB * 12) {
-        const int s = tid / 12, e = tid % 12, b = b0 + s;
-        if (b < batch) {
-            float* o = dA_part + ((size_t)split * batch + b) * 288;
-#pragma unroll
-            for (int j = 0; j < kJoints; ++j) o[j * 12 + e] = accA[j];
-        }
-    }
-    if (tid < kXPad) {
-#pragma unroll
-        for (int s = 0; s < TB; ++s)
-            if (b0 + s < batch) dx_part[((size_t)split * batch + b0 + s) * kXPad + tid] = accX[s];
-    }
-}
-
-cudaError_t launch_vertex_backward(const ModelView& M, const float* A, const float* vposed, const float* dverts,
-                                   float* dA_part, float* dx_part, int batch, int nsplit, cudaStream_t stream) {
-    if (batch <= 0) return cudaSuccess;
-    const size_t smem = (size_t)(kBwdTB * 288 + kTV * kJoints + kTV * kBwdTB * 12 + 3 * kTV * kBwdTB) * sizeof(float);
-    cudaError_t e = opt_in_smem(lbs_vertex_backward_kernel, smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(nsplit, (batch + kBwdTB - 1) / kBwdTB);
-    lbs_vertex_backward_kernel<<<grid, 256, smem, stream>>>(M, A, vposed, dverts, dA_part, dx_part, batch, nsplit);
     return cudaGetLastError();
 }
 

@@ -10,15 +10,10 @@ struct PoseParams;
 
 constexpr int kFitThreads = 384;
 constexpr int kPoseThreads = 384;
-constexpr int kMaxSplit = 8;
 
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream);
 cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
 cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
-cudaError_t launch_vertex_forward(const ModelView& M, const float* x, const float* A, float* verts, float* vposed,
-                                  int batch, cudaStream_t stream);
-cudaError_t launch_vertex_backward(const ModelView& M, const float* A, const float* vposed, const float* dverts,
-                                   float* dA_part, float* dx_part, int batch, int nsplit, cudaStream_t stream);
 cudaError_t launch_quat_rodrigues_fwd(const float* theta, float* rot, int n, cudaStream_t st);
 cudaError_t launch_quat_rodrigues_bwd(const float* theta, const float* grot, float* gtheta, int n, cudaStream_t st);
 cudaError_t launch_projection_fwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,

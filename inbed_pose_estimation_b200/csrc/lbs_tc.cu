@@ -1,14 +1,24 @@
-// Tensor-core LBS vertex forward for sm_100a: tcgen05.mma (kind::tf32, accumulators in TMEM) fed by TMA,
-// 3xTF32 operand splitting to keep fp32 accuracy.
+// Tensor-core LBS vertex path for sm_100a: tcgen05.mma (kind::tf32, fp32 accumulators in TMEM) fed by TMA, with
+// 3xTF32 operand splitting (every fp32 operand = hi + lo, hi = tf32(x); each k-step issues hi*hi + lo*hi + hi*lo)
+// to keep fp32 accuracy.  Restates smplx lbs and its gradient:
 //
-//   GEMM 1 (blend shapes, smplx lbs a6+a9):  v_posed[b, 3v+c] = sum_m x[b,m] * basis[m, 3v+c]     M=128 samples, N=96, K=224
-//   GEMM 2 (skinning, a11):                  T_e[b, v]        = sum_j A[b,j,e] * W[v,j], e<12      M=128 samples, N=32, K=24
-//   epilogue (CUDA cores, from TMEM):        verts[b,v,r]     = T[4r..4r+2][b,v] . v_posed[b,v,:] + T[4r+3][b,v]
+//   forward   blend GEMM   v_posed[b, 3v+c] = sum_m x[b,m] basis[m, 3v+c]                 tc_gemm_kernel<256, false>
+//             skinning     T[b,v,e] = sum_j W[v,j] A[b,j,e] ; verts = T [v_posed; 1]       tc_skin_kernel<0>
+//   backward  skinning^T   dvp[b,v,c] = sum_r T[b,v,r,c] dverts[b,v,r]                     tc_skin_kernel<1>
+//             dx GEMM      dx[b,m] = sum_col dvp[b,col] basis[m,col]                       tc_gemm_kernel<224, true>
+//             dA GEMM      dA[b,j,(r,c)] = sum_v W[v,j] dverts[b,v,r] [v_posed[b,v]; 1][c]  tc_dA_kernel
 //
-// One persistent CTA per SM walks (sample tile, vertex tile) pairs.  Warp roles: warp 0 = TMA producer,
-// warp 1 = MMA issuer (one elected thread), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter
-// = warp % 4).  3xTF32: every fp32 operand is pre-split into hi = tf32(x) and lo = x - hi; each k-step issues
-// hi*hi + lo*hi + hi*lo into the same fp32 TMEM accumulator.
+// Orientation is chosen per GEMM to minimise the operand bytes streamed from L2 (the binding resource once every
+// fp32 operand is doubled into hi/lo): K = 224 GEMMs put the samples on the 128 TMEM lanes, the K = 24 skinning
+// GEMMs put the VERTICES on the lanes so that the per-tile M operand is the small W block (24 values per row)
+// rather than the 288 transform entries per sample.  v_posed / dvp travel through HBM between the kernels.
+//
+// The tensor pipe truncates its fp32 accumulator after every MMA, a bias that grows with the accumulation chain;
+// chains are therefore bounded (<= 84 MMAs for the forward, <= 168 for the gradients) and longer reductions are
+// finished in fp32 registers (dx GEMM) or by summing per-split partials (dA GEMM) with round-to-nearest adds.
+//
+// All kernels are warp-specialised: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
+// allocator, warps 4.. = CUDA-core consumers / operand generators (TMEM lane quarter = warp % 4).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,280 +26,553 @@
 
 #include "launch.h"
 #include "lbs_tc.h"
+#include "tc_common.cuh"
 
 namespace smplb200 {
-
 namespace tc {
 
-constexpr int BM = 128;                 // samples per tile (UMMA M)
-constexpr int BV = 32;                  // vertices per tile
-constexpr int BN = 3 * BV;              // 96 coordinate columns (UMMA N of GEMM 1)
-constexpr int BK = 32;                  // tf32 elements per 128-byte swizzle row
-constexpr int KB = kXPad / BK;          // 7 k-blocks of GEMM 1
-constexpr int NE = 12;                  // entries of the 3x4 skinning transform
-constexpr int KJ = 3;                   // k-steps (of 8) covering the 24 joints
-constexpr int NVT = (kVerts + BV - 1) / BV;     // 216 vertex tiles
-constexpr int STAGES1 = 2, STAGES2 = 2;
-constexpr uint32_t X_BYTES = BM * BK * 4;       // 16384
-constexpr uint32_t B_BYTES = BN * BK * 4;       // 12288
-constexpr uint32_t W_BYTES = BV * BK * 4;       // 4096
-constexpr uint32_t STAGE1_BYTES = 2 * X_BYTES + 2 * B_BYTES;   // 57344
-constexpr uint32_t STAGE2_BYTES = 2 * X_BYTES;                 // 32768
-constexpr uint32_t OFF_RING1 = 0;
-constexpr uint32_t OFF_RING2 = OFF_RING1 + STAGES1 * STAGE1_BYTES;    // 114688
-constexpr uint32_t OFF_W = OFF_RING2 + STAGES2 * STAGE2_BYTES;        // 180224
-constexpr uint32_t OFF_BAR = OFF_W + 2 * W_BYTES;                     // 188416
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;                 // + barriers + alignment slack
-constexpr int TMEM_COLS = 512;
-constexpr int COL_T = BN;               // T_e accumulators start at column 96: 12 x 32 columns
-constexpr int THREADS = 256;
+constexpr int BM = 128;                  // UMMA M (TMEM lanes)
+constexpr int BK = 32;                   // tf32 elements per 128-byte swizzle row = one k-block
+constexpr uint32_t TILE128 = BM * BK * 4;   // 16384: a [128 x 32] fp32 operand tile
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct Barrier { uint64_t v; };
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    printf("lbs_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-    __trap();
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
-    return (1u << 4)            // D format F32
-           | (2u << 7)          // A format TF32
-           | (2u << 10)         // B format TF32
-           | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);      // K-major A and B (bits 15,16 = 0)
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// =====================================================================================================================
+// 3xTF32 GEMM  D[M x N] = A[M x K] . B[N x K]^T  (all K-major).  SPLITK = false: persistent over (m tile, n tile) items,
+// K short (one accumulation chain per item), epilogue TMEM -> smem -> TMA store, accumulators double buffered.
+// SPLITK = true: one (m tile, K range) item per CTA, chains of CHAIN k-blocks alternate between two TMEM buffers and are
+// added into fp32 registers by the flush warps; the partial result is written with plain stores.
+// =====================================================================================================================
+struct alignas(64) GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, out; };
+struct GemmWork {
+    int num_items;      // m tiles * n tiles * nsplit
+    int n_tiles;        // N tiles per m tile
+    int nsplit;         // K splits per (m tile, n tile)
+    int total_kb;       // k-blocks of the whole K extent
+    int chain;          // k-blocks per accumulation chain
+};
 
-struct Barriers {
-    uint64_t full1[STAGES1], empty1[STAGES1], full2[STAGES2], empty2[STAGES2];
-    uint64_t wfull, wempty, tmem_full, tmem_empty;
+template <int NT>
+struct GemmSmem {
+    static constexpr int STAGES = 2;
+    static constexpr uint32_t B_BYTES = NT * BK * 4;
+    static constexpr uint32_t STAGE_BYTES = 2 * TILE128 + 2 * B_BYTES;
+    static constexpr uint32_t OFF_OUT = STAGES * STAGE_BYTES;          // two [128 x 32] staging tiles for the TMA store
+    static constexpr uint32_t OFF_BAR = OFF_OUT + 2 * TILE128;
+    static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;            // + barriers + alignment slack
+    static_assert(B_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+    static_assert(BYTES <= 232448, "shared memory budget");
+};
+struct GemmBars {
+    uint64_t full[2], empty[2], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-lbs_vertex_forward_tc_kernel(const __grid_constant__ TcMaps maps, float* __restrict__ verts, float* __restrict__ vposed,
-                             int batch, int num_sample_tiles) {
+template <int NT, bool SPLITK>
+__global__ void __launch_bounds__(SPLITK ? 384 : 256, 1)
+tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float* __restrict__ out_direct, int batch) {
+    using SM = GemmSmem<NT>;
+    constexpr int STAGES = SM::STAGES;
+    constexpr int CONSUMER_WARPS = SPLITK ? 8 : 4;
     extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B operand tiles need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    Barriers* bars = reinterpret_cast<Barriers*>(smem + OFF_BAR);
+    GemmBars* bars = reinterpret_cast<GemmBars*>(smem + SM::OFF_BAR);
     const uint32_t s_base = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = num_sample_tiles * NVT;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES1; ++i) { mbar_init(smem_u32(&bars->full1[i]), 1); mbar_init(smem_u32(&bars->empty1[i]), 1); }
-        for (int i = 0; i < STAGES2; ++i) { mbar_init(smem_u32(&bars->full2[i]), 1); mbar_init(smem_u32(&bars->empty2[i]), 1); }
-        mbar_init(smem_u32(&bars->wfull), 1);
-        mbar_init(smem_u32(&bars->wempty), 1);
-        mbar_init(smem_u32(&bars->tmem_full), 1);
-        mbar_init(smem_u32(&bars->tmem_empty), 4);      // one arrival per epilogue warp
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), CONSUMER_WARPS); }
+        fence_barrier_init();
+        prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_hi); prefetch_tmap(&maps.b_lo);
+        if (!SPLITK) prefetch_tmap(&maps.out);
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
+    auto decode = [&](int item, int& mt, int& nt, int& sp, int& kb0, int& kb1) {
+        sp = item % work.nsplit;
+        const int t = item / work.nsplit;
+        nt = t % work.n_tiles;
+        mt = t / work.n_tiles;
+        kb0 = (int)(((long long)work.total_kb * sp) / work.nsplit);
+        kb1 = (int)(((long long)work.total_kb * (sp + 1)) / work.nsplit);
+    };
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t st1 = 0, ph1 = 0, st2 = 0, ph2 = 0, phw = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int stile = tile / NVT, vt = tile % NVT;
-                mbar_wait(smem_u32(&bars->wempty), phw ^ 1);
-                mbar_expect_tx(smem_u32(&bars->wfull), 2 * W_BYTES);
-                tma_load_2d(s_base + OFF_W, &maps.w_hi, smem_u32(&bars->wfull), 0, vt * BV);
-                tma_load_2d(s_base + OFF_W + W_BYTES, &maps.w_lo, smem_u32(&bars->wfull), 0, vt * BV);
-                phw ^= 1;
-                for (int s = 0; s < KB; ++s) {
-                    mbar_wait(smem_u32(&bars->empty1[st1]), ph1 ^ 1);
-                    const uint32_t full = smem_u32(&bars->full1[st1]);
-                    const uint32_t base = s_base + OFF_RING1 + st1 * STAGE1_BYTES;
-                    mbar_expect_tx(full, STAGE1_BYTES);
-                    tma_load_2d(base, &maps.x_hi, full, s * BK, stile * BM);
-                    tma_load_2d(base + X_BYTES, &maps.x_lo, full, s * BK, stile * BM);
-                    tma_load_2d(base + 2 * X_BYTES, &maps.b_hi, full, s * BK, vt * BN);
-                    tma_load_2d(base + 2 * X_BYTES + B_BYTES, &maps.b_lo, full, s * BK, vt * BN);
-                    if (++st1 == STAGES1) { st1 = 0; ph1 ^= 1; }
-                }
-                for (int e = 0; e < NE; ++e) {
-                    mbar_wait(smem_u32(&bars->empty2[st2]), ph2 ^ 1);
-                    const uint32_t full = smem_u32(&bars->full2[st2]);
-                    const uint32_t base = s_base + OFF_RING2 + st2 * STAGE2_BYTES;
-                    mbar_expect_tx(full, STAGE2_BYTES);
-                    tma_load_3d(base, &maps.ae_hi, full, 0, stile * BM, e);
-                    tma_load_3d(base + X_BYTES, &maps.ae_lo, full, 0, stile * BM, e);
-                    if (++st2 == STAGES2) { st2 = 0; ph2 ^= 1; }
+            Ring<STAGES> r;
+            for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {
+                int mt, nt, sp, kb0, kb1;
+                decode(item, mt, nt, sp, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(smem_u32(&bars->empty[r.stage]), r.phase ^ 1);
+                    const uint32_t full = smem_u32(&bars->full[r.stage]);
+                    const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
+                    mbar_expect_tx(full, SM::STAGE_BYTES);
+                    tma_load_2d(base, &maps.a_hi, full, kb * BK, mt * BM);
+                    tma_load_2d(base + TILE128, &maps.a_lo, full, kb * BK, mt * BM);
+                    tma_load_2d(base + 2 * TILE128, &maps.b_hi, full, kb * BK, nt * NT);
+                    tma_load_2d(base + 2 * TILE128 + SM::B_BYTES, &maps.b_lo, full, kb * BK, nt * NT);
+                    r.advance();
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc1 = instr_desc(BM, BN), idesc2 = instr_desc(BM, BV);
-            uint32_t st1 = 0, ph1 = 0, st2 = 0, ph2 = 0, phw = 0, pht = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(&bars->tmem_empty), pht ^ 1);        // epilogue drained the accumulators
-                tc_fence_after();
-                for (int s = 0; s < KB; ++s) {
-                    mbar_wait(smem_u32(&bars->full1[st1]), ph1);
+            constexpr uint32_t idesc = instr_desc(BM, NT);
+            Ring<STAGES> r;
+            Ring<2> t;
+            for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {
+                int mt, nt, sp, kb0, kb1;
+                decode(item, mt, nt, sp, kb0, kb1);
+                for (int g0 = kb0; g0 < kb1; g0 += work.chain) {
+                    const int g1 = (g0 + work.chain < kb1) ? g0 + work.chain : kb1;
+                    mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);       // consumers drained this accumulator
                     tc_fence_after();
-                    const uint32_t base = s_base + OFF_RING1 + st1 * STAGE1_BYTES;
-                    const uint64_t d_xh = smem_desc(base), d_xl = smem_desc(base + X_BYTES);
-                    const uint64_t d_bh = smem_desc(base + 2 * X_BYTES), d_bl = smem_desc(base + 2 * X_BYTES + B_BYTES);
+                    const uint32_t tm = tmem_base + t.stage * NT;
+                    for (int kb = g0; kb < g1; ++kb) {
+                        mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
+                        tc_fence_after();
+                        const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
+                        const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + TILE128);
+                        const uint64_t d_bh = smem_desc(base + 2 * TILE128), d_bl = smem_desc(base + 2 * TILE128 + SM::B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);          // 32 bytes per k-step, in 16-byte units
-                        umma_tf32(tmem_base, d_xh + ko, d_bh + ko, idesc1, (s | k) != 0);
-                        umma_tf32(tmem_base, d_xl + ko, d_bh + ko, idesc1, 1);
-                        umma_tf32(tmem_base, d_xh + ko, d_bl + ko, idesc1, 1);
+                        for (int k = 0; k < BK / 8; ++k) {
+                            const uint64_t ko = (uint64_t)(k * 2);          // 32 bytes per k-step, in 16-byte units
+                            umma_tf32(tm, d_ah + ko, d_bh + ko, idesc, (kb != g0 || k != 0) ? 1u : 0u);
+                            umma_tf32(tm, d_al + ko, d_bh + ko, idesc, 1);
+                            umma_tf32(tm, d_ah + ko, d_bl + ko, idesc, 1);
+                        }
+                        umma_commit(smem_u32(&bars->empty[r.stage]));
+                        r.advance();
                     }
-                    umma_commit(smem_u32(&bars->empty1[st1]));
-                    if (++st1 == STAGES1) { st1 = 0; ph1 ^= 1; }
+                    umma_commit(smem_u32(&bars->tmem_full[t.stage]));
+                    t.advance();
                 }
-                mbar_wait(smem_u32(&bars->wfull), phw);
-                tc_fence_after();
-                phw ^= 1;
-                const uint64_t d_wh = smem_desc(s_base + OFF_W), d_wl = smem_desc(s_base + OFF_W + W_BYTES);
-                for (int e = 0; e < NE; ++e) {
-                    mbar_wait(smem_u32(&bars->full2[st2]), ph2);
-                    tc_fence_after();
-                    const uint32_t base = s_base + OFF_RING2 + st2 * STAGE2_BYTES;
-                    const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + X_BYTES);
-                    const uint32_t tm = tmem_base + COL_T + e * BV;
-#pragma unroll
-                    for (int k = 0; k < KJ; ++k) {
-                        const uint64_t ko = (uint64_t)(k * 2);
-                        umma_tf32(tm, d_ah + ko, d_wh + ko, idesc2, k != 0);
-                        umma_tf32(tm, d_al + ko, d_wh + ko, idesc2, 1);
-                        umma_tf32(tm, d_ah + ko, d_wl + ko, idesc2, 1);
-                    }
-                    umma_commit(smem_u32(&bars->empty2[st2]));
-                    if (++st2 == STAGES2) { st2 = 0; ph2 ^= 1; }
-                }
-                umma_commit(smem_u32(&bars->wempty));
-                umma_commit(smem_u32(&bars->tmem_full));
-                pht ^= 1;
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue: TMEM -> registers -> skinning -> HBM =================
+        // ================= consumers: TMEM -> registers -> HBM =================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t pht = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int stile = tile / NVT, vt = tile % NVT;
-            const int b = stile * BM + row;
-            mbar_wait(smem_u32(&bars->tmem_full), pht);
-            tc_fence_after();
-            pht ^= 1;
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        Ring<2> t;
+        if constexpr (!SPLITK) {
+            const int epi_tid = threadIdx.x - 128;
+            float* staging = reinterpret_cast<float*>(smem + SM::OFF_OUT);
+            uint32_t cc = 0;
+            for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {
+                int mt, nt, sp, kb0, kb1;
+                decode(item, mt, nt, sp, kb0, kb1);
+                mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BV / 8; ++c) {
-                float vp[24], T[NE][8];
-                tmem_ld8(t_lane + 24 * c, vp);
-                tmem_ld8(t_lane + 24 * c + 8, vp + 8);
-                tmem_ld8(t_lane + 24 * c + 16, vp + 16);
+                for (int ch = 0; ch < NT / 32; ++ch, ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem_base + lane_bits + t.stage * NT + ch * 32, v);
+                    tmem_ld_wait();
+                    if (epi_tid == 0) tma_store_wait_read<1>();          // the store that last read this staging tile is done
+                    named_bar_sync(1, 128);
+                    float* sbuf = staging + (cc & 1) * (TILE128 / 4);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) tmem_ld8(t_lane + COL_T + e * BV + 8 * c, T[e]);
-                tmem_ld_wait();
-                float out[24];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        out[3 * i + r] = T[4 * r][i] * vp[3 * i] + T[4 * r + 1][i] * vp[3 * i + 1] + T[4 * r + 2][i] * vp[3 * i + 2] + T[4 * r + 3][i];
-                const int v0 = vt * BV + 8 * c;
-                if (b < batch) {
-                    float* o = verts + (size_t)b * kCols + 3 * v0;          // 8-byte aligned (82680 = 8 * 10335)
-                    float* p = vposed ? vposed + (size_t)b * kCols + 3 * v0 : nullptr;
-                    if (v0 + 8 <= kVerts) {
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) reinterpret_cast<float2*>(o)[i] = make_float2(out[2 * i], out[2 * i + 1]);
-                        if (p) {
-#pragma unroll
-                            for (int i = 0; i < 12; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(vp[2 * i], vp[2 * i + 1]);
-                        }
-                    } else {
-                        for (int i = 0; i < 24; ++i)
-                            if (3 * v0 + i < kCols) {
-                                o[i] = out[i];
-                                if (p) p[i] = vp[i];
-                            }
+                    for (int c = 0; c < 8; ++c)
+                        *reinterpret_cast<float4*>(sbuf + swz128(row, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    fence_proxy_async();
+                    named_bar_sync(1, 128);
+                    if (epi_tid == 0) {
+                        tma_store_3d(&maps.out, smem_u32(sbuf), nt * NT + ch * 32, mt * BM, sp);
+                        tma_store_commit();
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[t.stage]));
+                t.advance();
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty));
+            if (epi_tid == 0) tma_store_wait_all<0>();
+        } else {
+            constexpr int HALF = NT / 2;                      // columns per flush warp (two warps share a lane quarter)
+            static_assert(HALF % 16 == 0, "flush width");
+            const int half = (warp - 4) >> 2;
+            float acc[HALF];
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+            for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {       // one item per CTA in practice
+                int mt, nt, sp, kb0, kb1;
+                decode(item, mt, nt, sp, kb0, kb1);
+                for (int g0 = kb0; g0 < kb1; g0 += work.chain) {
+                    mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + lane_bits + t.stage * NT + half * HALF;
+#pragma unroll
+                    for (int c = 0; c < HALF / 8; ++c) {
+                        float v[8];
+                        tmem_ld8(ta + 8 * c, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[8 * c + i] += v[i];
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[t.stage]));
+                    t.advance();
+                }
+                const int b = mt * BM + row;
+                if (b < batch) {
+                    float4* o = reinterpret_cast<float4*>(out_direct + ((size_t)sp * batch + b) * NT + half * HALF);
+#pragma unroll
+                    for (int c = 0; c < HALF / 4; ++c) o[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+                }
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =====================================================================================================================
+// Skinning GEMM with the vertices on the TMEM lanes:  T^T[v, (b, e)] = sum_j W[v, j] A[b, e, j]   (M = 128 vertices,
+// N = 16 samples x 12 entries = 192, K = 24 padded to 32) and the per-vertex transform applied by the consumer warps.
+// A CTA owns one 128-vertex block (W tile resident) and walks over sample chunks g, g + groups, ...
+// MODE 0: verts[b][v][r] = T[r][0..2] . vp[b][v] + T[r][3]        MODE 1: dvp[b][v][c] = sum_r T[r][c] dverts[b][v][r]
+// =====================================================================================================================
+struct alignas(64) SkinMaps { CUtensorMap w_hi, w_lo, ae_hi, ae_lo; };
+constexpr int SK_NB = 16;                          // samples per chunk
+constexpr int SK_N = SK_NB * 12;                   // 192 accumulator columns
+constexpr int SK_STAGES = 3;
+constexpr uint32_t SK_AE_BYTES = SK_N * BK * 4;    // 24576
+constexpr uint32_t SK_STAGE_BYTES = 2 * SK_AE_BYTES;
+constexpr uint32_t SK_OFF_RING = 2 * TILE128;
+constexpr uint32_t SK_OFF_BAR = SK_OFF_RING + SK_STAGES * SK_STAGE_BYTES;
+constexpr uint32_t SK_SMEM = SK_OFF_BAR + 256 + 1024;
+constexpr int SK_VBLOCKS = kTcVertRowsPad / BM;    // 54
+struct SkinBars {
+    uint64_t wfull, full[SK_STAGES], empty[SK_STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(384, 1)
+tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ in, float* __restrict__ out0, float* __restrict__ out1,
+               int batch, int groups) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    SkinBars* bars = reinterpret_cast<SkinBars*>(smem + SK_OFF_BAR);
+    const uint32_t s_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vb = blockIdx.x % SK_VBLOCKS, g = blockIdx.x / SK_VBLOCKS;
+    const int nchunks = (batch + SK_NB - 1) / SK_NB;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(smem_u32(&bars->wfull), 1);
+        for (int i = 0; i < SK_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), 8); }
+        fence_barrier_init();
+        prefetch_tmap(&maps.w_hi); prefetch_tmap(&maps.w_lo); prefetch_tmap(&maps.ae_hi); prefetch_tmap(&maps.ae_lo);
+    }
+    if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t wfull = smem_u32(&bars->wfull);
+            mbar_expect_tx(wfull, 2 * TILE128);
+            tma_load_2d(s_base, &maps.w_hi, wfull, 0, vb * BM);
+            tma_load_2d(s_base + TILE128, &maps.w_lo, wfull, 0, vb * BM);
+            Ring<SK_STAGES> r;
+            for (int c = g; c < nchunks; c += groups) {
+                mbar_wait(smem_u32(&bars->empty[r.stage]), r.phase ^ 1);
+                const uint32_t full = smem_u32(&bars->full[r.stage]);
+                const uint32_t base = s_base + SK_OFF_RING + r.stage * SK_STAGE_BYTES;
+                mbar_expect_tx(full, SK_STAGE_BYTES);
+                tma_load_2d(base, &maps.ae_hi, full, 0, c * SK_N);
+                tma_load_2d(base + SK_AE_BYTES, &maps.ae_lo, full, 0, c * SK_N);
+                r.advance();
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(BM, SK_N);
+            const uint64_t d_wh = smem_desc(s_base), d_wl = smem_desc(s_base + TILE128);
+            mbar_wait(smem_u32(&bars->wfull), 0);
+            tc_fence_after();
+            Ring<SK_STAGES> r;
+            Ring<2> t;
+            for (int c = g; c < nchunks; c += groups) {
+                mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);
+                mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
+                tc_fence_after();
+                const uint32_t base = s_base + SK_OFF_RING + r.stage * SK_STAGE_BYTES;
+                const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + SK_AE_BYTES);
+                const uint32_t tm = tmem_base + t.stage * SK_N;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {                 // 24 joints = 3 k-steps of 8
+                    const uint64_t ko = (uint64_t)(k * 2);
+                    umma_tf32(tm, d_wh + ko, d_ah + ko, idesc, k != 0);
+                    umma_tf32(tm, d_wl + ko, d_ah + ko, idesc, 1);
+                    umma_tf32(tm, d_wh + ko, d_al + ko, idesc, 1);
+                }
+                umma_commit(smem_u32(&bars->empty[r.stage]));
+                umma_commit(smem_u32(&bars->tmem_full[t.stage]));
+                r.advance();
+                t.advance();
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int v = vb * BM + q * 32 + lane;
+        const bool vok = v < kVerts;
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+        Ring<2> t;
+        for (int c = g; c < nchunks; c += groups) {
+            const int b0 = c * SK_NB + half * 8;
+            float iv[8][3];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = b0 + i;
+                if (MODE == 0) {
+                    const bool ok = b < batch;                           // pitch covers the padded vertices
+                    const float* p = in + (size_t)b * kVpPitch + 3 * v;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) iv[i][a] = ok ? __ldg(p + a) : 0.f;
+                } else {
+                    const bool ok = vok && b < batch;
+                    const float* p = in + (size_t)b * kCols + 3 * v;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) iv[i][a] = ok ? __ldg(p + a) : 0.f;
+                }
+            }
+            mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + lane_bits + t.stage * SK_N + half * 96;
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {                  // two samples (24 columns) per round
+                float T[24];
+                tmem_ld8(ta + 24 * pr, T);
+                tmem_ld8(ta + 24 * pr + 8, T + 8);
+                tmem_ld8(ta + 24 * pr + 16, T + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = 2 * pr + u, b = b0 + i;
+                    const float* Tt = T + 12 * u;
+                    const float a0 = iv[i][0], a1 = iv[i][1], a2 = iv[i][2];
+                    if (MODE == 0) {
+                        if (vok && b < batch) {
+                            float* o = out0 + (size_t)b * kCols + 3 * v;
+                            o[0] = Tt[0] * a0 + Tt[1] * a1 + Tt[2] * a2 + Tt[3];
+                            o[1] = Tt[4] * a0 + Tt[5] * a1 + Tt[6] * a2 + Tt[7];
+                            o[2] = Tt[8] * a0 + Tt[9] * a1 + Tt[10] * a2 + Tt[11];
+                        }
+                    } else {
+                        if (b < batch) {                                 // padded vertices get zeros (dverts masked above)
+                            float* oh = out0 + (size_t)b * kVpPitch + 3 * v;
+                            float* ol = out1 + (size_t)b * kVpPitch + 3 * v;
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) {
+                                const float d = Tt[cc] * a0 + Tt[4 + cc] * a1 + Tt[8 + cc] * a2;
+                                const float hi = tf32_round(d);
+                                oh[cc] = hi;
+                                ol[cc] = d - hi;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[t.stage]));
+            t.advance();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// =====================================================================================================================
+// dA GEMM with operands generated on chip:  D_e[b, j] = sum_v P_e[b, v] W[v, j],  P_(r,c)[b, v] = dverts[b,v,r] [vp[b,v]; 1][c]
+// (M = 128 samples, N = 24 joints padded to 32, K = the split's vertex range in k-blocks of 32; 12 accumulators of 32
+// columns).  Generator warps read dverts / v_posed rows, form the 12 product tiles of a k-block, split them into hi / lo
+// and store them in the swizzled UMMA layout; the MMA warp consumes them through a 4-stage ring.
+// =====================================================================================================================
+struct alignas(64) DaMaps { CUtensorMap wT_hi, wT_lo; };
+constexpr int DA_PSTAGES = 4, DA_WSTAGES = 2;
+constexpr uint32_t DA_P_STAGE = 2 * TILE128;                   // P_hi | P_lo
+constexpr uint32_t DA_W_TILE = 32 * BK * 4;                    // 4096
+constexpr uint32_t DA_OFF_W = DA_PSTAGES * DA_P_STAGE;         // 131072
+constexpr uint32_t DA_OFF_BAR = DA_OFF_W + DA_WSTAGES * 2 * DA_W_TILE;
+constexpr uint32_t DA_SMEM = DA_OFF_BAR + 256 + 1024;
+constexpr int DA_KBLOCKS = kTcVertRowsPad / BK;                // 216
+struct DaBars {
+    uint64_t wfull[DA_WSTAGES], wempty[DA_WSTAGES], pfull[DA_PSTAGES], pempty[DA_PSTAGES], acc_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(384, 1)
+tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dverts, const float* __restrict__ vposed,
+             float* __restrict__ dA_part, int batch, int nsplit) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    DaBars* bars = reinterpret_cast<DaBars*>(smem + DA_OFF_BAR);
+    const uint32_t s_base = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp = blockIdx.x, st = blockIdx.y;
+    const int kb0 = (DA_KBLOCKS * sp) / nsplit, kb1 = (DA_KBLOCKS * (sp + 1)) / nsplit;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < DA_WSTAGES; ++i) { mbar_init(smem_u32(&bars->wfull[i]), 1); mbar_init(smem_u32(&bars->wempty[i]), 1); }
+        for (int i = 0; i < DA_PSTAGES; ++i) { mbar_init(smem_u32(&bars->pfull[i]), 8); mbar_init(smem_u32(&bars->pempty[i]), 1); }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        fence_barrier_init();
+        prefetch_tmap(&maps.wT_hi); prefetch_tmap(&maps.wT_lo);
+    }
+    if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            Ring<DA_WSTAGES> r;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&bars->wempty[r.stage]), r.phase ^ 1);
+                const uint32_t full = smem_u32(&bars->wfull[r.stage]);
+                const uint32_t base = s_base + DA_OFF_W + r.stage * 2 * DA_W_TILE;
+                mbar_expect_tx(full, 2 * DA_W_TILE);
+                tma_load_2d(base, &maps.wT_hi, full, kb * BK, 0);
+                tma_load_2d(base + DA_W_TILE, &maps.wT_lo, full, kb * BK, 0);
+                r.advance();
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc(BM, 32);
+            Ring<DA_WSTAGES> wr;
+            Ring<DA_PSTAGES> pr;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(smem_u32(&bars->wfull[wr.stage]), wr.phase);
+                tc_fence_after();
+                const uint32_t wbase = s_base + DA_OFF_W + wr.stage * 2 * DA_W_TILE;
+                const uint64_t d_wh = smem_desc(wbase), d_wl = smem_desc(wbase + DA_W_TILE);
+#pragma unroll 1
+                for (int e = 0; e < 12; ++e) {
+                    mbar_wait(smem_u32(&bars->pfull[pr.stage]), pr.phase);
+                    tc_fence_after();
+                    const uint32_t pbase = s_base + pr.stage * DA_P_STAGE;
+                    const uint64_t d_ph = smem_desc(pbase), d_pl = smem_desc(pbase + TILE128);
+                    const uint32_t tm = tmem_base + e * 32;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t ko = (uint64_t)(k * 2);
+                        umma_tf32(tm, d_ph + ko, d_wh + ko, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        umma_tf32(tm, d_pl + ko, d_wh + ko, idesc, 1);
+                        umma_tf32(tm, d_ph + ko, d_wl + ko, idesc, 1);
+                    }
+                    umma_commit(smem_u32(&bars->pempty[pr.stage]));
+                    pr.advance();
+                }
+                umma_commit(smem_u32(&bars->wempty[wr.stage]));
+                wr.advance();
+            }
+            umma_commit(smem_u32(&bars->acc_full));
+        }
+    } else if (warp >= 4) {
+        // ================= operand generators (8 warps): thread = (sample row, half of the k-block's 32 vertices) =================
+        const int gt = threadIdx.x - 128;
+        const int rowl = gt & 127, h = gt >> 7;
+        const int b = st * BM + rowl;
+        const bool bok = b < batch;
+        float* ring = reinterpret_cast<float*>(smem);
+        Ring<DA_PSTAGES> pr;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int col0 = 3 * (kb * BK + h * 16);                    // first coordinate column of this thread's 16 vertices
+            float dv[48], vp[48];
+            {
+                const float2* pd = reinterpret_cast<const float2*>(dverts + (size_t)b * kCols + col0);
+                const float4* pv = reinterpret_cast<const float4*>(vposed + (size_t)b * kVpPitch + col0);
+#pragma unroll
+                for (int i = 0; i < 24; ++i) {
+                    float2 t = make_float2(0.f, 0.f);
+                    if (bok && col0 + 2 * i + 1 < kCols) t = __ldg(pd + i);
+                    dv[2 * i] = t.x; dv[2 * i + 1] = t.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bok) t = __ldg(pv + i);
+                    vp[4 * i] = t.x; vp[4 * i + 1] = t.y; vp[4 * i + 2] = t.z; vp[4 * i + 3] = t.w;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int r = e >> 2, c = e & 3;
+                float hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p = (c < 3) ? dv[3 * i + r] * vp[3 * i + c] : dv[3 * i + r];
+                    hi[i] = tf32_round(p);
+                    lo[i] = p - hi[i];
+                }
+                mbar_wait(smem_u32(&bars->pempty[pr.stage]), pr.phase ^ 1);
+                float* ph = ring + pr.stage * (DA_P_STAGE / 4);
+                float* pl = ph + TILE128 / 4;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint32_t o = swz128(rowl, 4 * h + qq);
+                    *reinterpret_cast<float4*>(ph + o) = make_float4(hi[4 * qq], hi[4 * qq + 1], hi[4 * qq + 2], hi[4 * qq + 3]);
+                    *reinterpret_cast<float4*>(pl + o) = make_float4(lo[4 * qq], lo[4 * qq + 1], lo[4 * qq + 2], lo[4 * qq + 3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->pfull[pr.stage]));
+                pr.advance();
+            }
+        }
+        // ================= epilogue (warps 4..7): D_e[b][0..23] -> dA_part[split][b][e][24] =================
+        if (warp < 8) {
+            const int q = warp & 3;
+            const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+            mbar_wait(smem_u32(&bars->acc_full), 0);
+            tc_fence_after();
+            const int bb = st * BM + q * 32 + lane;
+#pragma unroll 1
+            for (int e = 0; e < 12; ++e) {
+                float v[32];
+                tmem_ld32(tmem_base + lane_bits + e * 32, v);
+                tmem_ld_wait();
+                if (bb < batch) {
+                    float4* o = reinterpret_cast<float4*>(dA_part + (((size_t)sp * batch + bb) * 12 + e) * kJoints);
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -312,7 +595,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 row-major [rows][cols] (optionally x planes), box = 32 columns (128 bytes) x box_rows, SWIZZLE_128B
+// fp32 row-major [planes][rows][cols] (planes = 0: two-dimensional), box = 32 columns (128 bytes) x box_rows, SWIZZLE_128B
 static bool make_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t planes, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -326,31 +609,130 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool tc_make_constant_maps(TcMaps* maps, const float* basisT_hi, const float* basisT_lo, const float* w_hi, const float* w_lo) {
-    return make_map(&maps->b_hi, basisT_hi, kXPad, kColsPad, 0, tc::BN) && make_map(&maps->b_lo, basisT_lo, kXPad, kColsPad, 0, tc::BN) &&
-           make_map(&maps->w_hi, w_hi, 32, kTcVertRowsPad, 0, tc::BV) && make_map(&maps->w_lo, w_lo, 32, kTcVertRowsPad, 0, tc::BV);
+bool tc_make_constant_maps(TcConstMaps* m, const float* basisT_hi, const float* basisT_lo, const float* basis_hi,
+                           const float* basis_lo, const float* w_hi, const float* w_lo, const float* wT_hi, const float* wT_lo) {
+    return make_map(&m->bT_hi, basisT_hi, kXPad, kColsPad, 0, 256) && make_map(&m->bT_lo, basisT_lo, kXPad, kColsPad, 0, 256) &&
+           make_map(&m->bm_hi, basis_hi, kColsPad, kXPad, 0, 224) && make_map(&m->bm_lo, basis_lo, kColsPad, kXPad, 0, 224) &&
+           make_map(&m->w_hi, w_hi, 32, kTcVertRowsPad, 0, 128) && make_map(&m->w_lo, w_lo, 32, kTcVertRowsPad, 0, 128) &&
+           make_map(&m->wT_hi, wT_hi, kTcVertRowsPad, 32, 0, 32) && make_map(&m->wT_lo, wT_lo, kTcVertRowsPad, 32, 0, 32);
 }
 
-cudaError_t launch_vertex_forward_tc(const TcMaps& constant_maps, const TcOperands& op, float* verts, float* vposed, int batch,
-                                     cudaStream_t stream) {
-    if (batch <= 0) return cudaSuccess;
-    TcMaps maps = constant_maps;
-    if (!make_map(&maps.x_hi, op.x_hi, kXPad, (uint64_t)batch, 0, tc::BM) || !make_map(&maps.x_lo, op.x_lo, kXPad, (uint64_t)batch, 0, tc::BM) ||
-        !make_map(&maps.ae_hi, op.ae_hi, 32, (uint64_t)batch, tc::NE, tc::BM) ||
-        !make_map(&maps.ae_lo, op.ae_lo, 32, (uint64_t)batch, tc::NE, tc::BM))
-        return cudaErrorInvalidValue;
+static int sm_count() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaError_t e = cudaFuncSetAttribute(tc::lbs_vertex_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+    return sms;
+}
+
+template <typename K>
+static cudaError_t opt_in(K kernel, uint32_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t launch_blend_gemm(const TcConstMaps& cm, const float* x_hi, const float* x_lo, float* vposed, int batch, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    constexpr int NT = 256;
+    tc::GemmMaps maps;
+    maps.b_hi = cm.bT_hi;
+    maps.b_lo = cm.bT_lo;
+    if (!make_map(&maps.a_hi, x_hi, kXPad, (uint64_t)batch, 0, tc::BM) || !make_map(&maps.a_lo, x_lo, kXPad, (uint64_t)batch, 0, tc::BM) ||
+        !make_map(&maps.out, vposed, kVpPitch, (uint64_t)batch, 1, tc::BM))
+        return cudaErrorInvalidValue;
+    tc::GemmWork w;
+    const int mtiles = (batch + tc::BM - 1) / tc::BM;
+    w.n_tiles = kColsPad / NT;           // 81
+    w.nsplit = 1;
+    w.total_kb = kXPad / tc::BK;         // 7
+    w.chain = w.total_kb;
+    w.num_items = mtiles * w.n_tiles;
+    cudaError_t e = opt_in(tc::tc_gemm_kernel<NT, false>, tc::GemmSmem<NT>::BYTES);
     if (e != cudaSuccess) return e;
-    const int stiles = (batch + tc::BM - 1) / tc::BM;
-    const int tiles = stiles * tc::NVT;
-    const int grid = tiles < sms ? tiles : sms;
-    tc::lbs_vertex_forward_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(maps, verts, vposed, batch, stiles);
+    const int grid = w.num_items < sm_count() ? w.num_items : sm_count();
+    tc::tc_gemm_kernel<NT, false><<<grid, 256, tc::GemmSmem<NT>::BYTES, stream>>>(maps, w, nullptr, batch);
+    return cudaGetLastError();
+}
+
+int tc_dx_splits(int batch) {
+    const int mtiles = (batch + tc::BM - 1) / tc::BM;
+    int n = (sm_count() + mtiles - 1) / mtiles;
+    if (n < 1) n = 1;
+    if (n > kMaxSplitX) n = kMaxSplitX;
+    return n;
+}
+
+cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const float* dvp_lo, float* dx_part, int batch, int nsplit,
+                           cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    constexpr int NT = 224;
+    tc::GemmMaps maps;
+    maps.b_hi = cm.bm_hi;
+    maps.b_lo = cm.bm_lo;
+    if (!make_map(&maps.a_hi, dvp_hi, kVpPitch, (uint64_t)batch, 0, tc::BM) || !make_map(&maps.a_lo, dvp_lo, kVpPitch, (uint64_t)batch, 0, tc::BM))
+        return cudaErrorInvalidValue;
+    maps.out = maps.a_hi;                // unused by the split-K epilogue
+    tc::GemmWork w;
+    const int mtiles = (batch + tc::BM - 1) / tc::BM;
+    w.n_tiles = 1;
+    w.nsplit = nsplit;
+    w.total_kb = kVpPitch / tc::BK;      // 648
+    w.chain = 7;                          // 84 MMAs per accumulation chain
+    w.num_items = mtiles * nsplit;
+    cudaError_t e = opt_in(tc::tc_gemm_kernel<NT, true>, tc::GemmSmem<NT>::BYTES);
+    if (e != cudaSuccess) return e;
+    tc::tc_gemm_kernel<NT, true><<<w.num_items, 384, tc::GemmSmem<NT>::BYTES, stream>>>(maps, w, dx_part, batch);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_skin(int mode, const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* in, float* out0,
+                               float* out1, int batch, cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    tc::SkinMaps maps;
+    maps.w_hi = cm.w_hi;
+    maps.w_lo = cm.w_lo;
+    if (!make_map(&maps.ae_hi, ae_hi, 32, (uint64_t)batch * 12, 0, tc::SK_N) || !make_map(&maps.ae_lo, ae_lo, 32, (uint64_t)batch * 12, 0, tc::SK_N))
+        return cudaErrorInvalidValue;
+    const int nchunks = (batch + tc::SK_NB - 1) / tc::SK_NB;
+    int groups = (2 * sm_count() + tc::SK_VBLOCKS - 1) / tc::SK_VBLOCKS;      // about two CTAs' worth of work per SM
+    if (groups > nchunks) groups = nchunks;
+    if (groups < 1) groups = 1;
+    cudaError_t e = mode == 0 ? opt_in(tc::tc_skin_kernel<0>, tc::SK_SMEM) : opt_in(tc::tc_skin_kernel<1>, tc::SK_SMEM);
+    if (e != cudaSuccess) return e;
+    const int grid = tc::SK_VBLOCKS * groups;
+    if (mode == 0) tc::tc_skin_kernel<0><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, batch, groups);
+    else tc::tc_skin_kernel<1><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, batch, groups);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_skin_forward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* vposed, float* verts,
+                                int batch, cudaStream_t stream) {
+    return launch_skin(0, cm, ae_hi, ae_lo, vposed, verts, nullptr, batch, stream);
+}
+cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp_hi,
+                                 float* dvp_lo, int batch, cudaStream_t stream) {
+    return launch_skin(1, cm, ae_hi, ae_lo, dverts, dvp_hi, dvp_lo, batch, stream);
+}
+
+int tc_dA_splits(int batch) {
+    const int mtiles = (batch + tc::BM - 1) / tc::BM;
+    int n = (sm_count() + mtiles - 1) / mtiles;
+    if (n < 16) n = 16;                   // <= 14 k-blocks (168 MMAs) per accumulation chain
+    if (n > kMaxSplitA) n = kMaxSplitA;
+    return n;
+}
+
+cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts, const float* vposed, float* dA_part, int batch, int nsplit,
+                      cudaStream_t stream) {
+    if (batch <= 0) return cudaSuccess;
+    tc::DaMaps maps;
+    maps.wT_hi = cm.wT_hi;
+    maps.wT_lo = cm.wT_lo;
+    cudaError_t e = opt_in(tc::tc_dA_kernel, tc::DA_SMEM);
+    if (e != cudaSuccess) return e;
+    dim3 grid(nsplit, (batch + tc::BM - 1) / tc::BM);
+    tc::tc_dA_kernel<<<grid, 384, tc::DA_SMEM, stream>>>(maps, dverts, vposed, dA_part, batch, nsplit);
     return cudaGetLastError();
 }
 

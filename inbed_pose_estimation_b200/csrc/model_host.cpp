@@ -120,21 +120,27 @@ std::string build_host_model(const smplb200_model_desc& d, HostModel& H) {
     memcpy(H.weights.data(), d.weights, sizeof(float) * (size_t)kVerts * kJoints);
 
     // ---- tf32 hi/lo split of the tensor-core operands (3xTF32) ------------------------------------------
-    H.basisT_hi.assign(H.basisT.size(), 0.f);
-    H.basisT_lo.assign(H.basisT.size(), 0.f);
-    for (size_t i = 0; i < H.basisT.size(); ++i) {
-        const float hi = tf32_round(H.basisT[i]);
-        H.basisT_hi[i] = hi;
-        H.basisT_lo[i] = H.basisT[i] - hi;
-    }
-    H.w_hi.assign((size_t)kTcVertRowsPad * 32, 0.f);
-    H.w_lo.assign((size_t)kTcVertRowsPad * 32, 0.f);
-    for (int v = 0; v < kVerts; ++v)
-        for (int j = 0; j < kJoints; ++j) {
-            const float w = d.weights[(size_t)v * kJoints + j], hi = tf32_round(w);
-            H.w_hi[(size_t)v * 32 + j] = hi;
-            H.w_lo[(size_t)v * 32 + j] = w - hi;
+    auto split = [](const std::vector<float>& src, std::vector<float>& hi, std::vector<float>& lo) {
+        hi.assign(src.size(), 0.f);
+        lo.assign(src.size(), 0.f);
+        for (size_t i = 0; i < src.size(); ++i) {
+            hi[i] = tf32_round(src[i]);
+            lo[i] = src[i] - hi[i];
         }
+    };
+    split(H.basisT, H.basisT_hi, H.basisT_lo);
+    split(H.basis, H.basis_hi, H.basis_lo);
+    {
+        std::vector<float> w32((size_t)kTcVertRowsPad * 32, 0.f), wT((size_t)32 * kTcVertRowsPad, 0.f);
+        for (int v = 0; v < kVerts; ++v)
+            for (int j = 0; j < kJoints; ++j) {
+                const float w = d.weights[(size_t)v * kJoints + j];
+                w32[(size_t)v * 32 + j] = w;
+                wT[(size_t)j * kTcVertRowsPad + v] = w;
+            }
+        split(w32, H.w_hi, H.w_lo);
+        split(wT, H.wT_hi, H.wT_lo);
+    }
 
     // ---- rest joints: J0 + JS.beta ------------------------------------------------------------------
     H.J0.assign(72, 0.f);

@@ -65,7 +65,9 @@ class _SMPLFunction(torch.autograd.Function):
         verts = torch.empty((B, constants.NUM_VERTS, 3), device=dev, dtype=torch.float32) if need_vertices else None
         joints = torch.empty((B, constants.NUM_JOINTS_OUT, 3), device=dev, dtype=torch.float32)
         needs_grad = bool(ctx.needs_input_grad[1] or ctx.needs_input_grad[2])   # forward runs under no_grad
-        vposed = torch.empty_like(verts) if (needs_grad and need_vertices) else None
+        # v_posed of the forward pass, kept for the backward call: [B][20736] (padded, 16-byte aligned rows - TMA target)
+        vposed = (torch.empty((B, _native.VPOSED_PITCH), device=dev, dtype=torch.float32)
+                  if (needs_grad and need_vertices) else None)
         ws = module.workspace(dev, B)
         with torch.cuda.device(dev):
             if B > 0:

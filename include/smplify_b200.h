@@ -32,6 +32,7 @@ extern "C" {
 #define SMPLB200_NUM_OUT_JOINTS 49
 #define SMPLB200_NUM_GAUSSIANS 8
 #define SMPLB200_MAX_ITERS 256
+#define SMPLB200_VPOSED_PITCH 20736 /* floats per sample of the saved v_posed buffer (3*6890 padded; rows 16-byte aligned) */
 
 typedef struct smplb200_model smplb200_model;
 
@@ -94,10 +95,12 @@ int smplb200_smplify_fitting_loss(const smplb200_model* model, int batch, float 
 
 /* SMPL.forward (models/smpl.py:21-33 -> smplx lbs).  rotmat_mode 0: pose is axis-angle [B][72]
  * (global_orient ++ body_pose); 1: pose is [B][24][3][3] (pose2rot=False).  saved_vposed
- * ([B][6890][3] or NULL) keeps v_posed for smplb200_smpl_backward. */
+ * ([B][SMPLB200_VPOSED_PITCH] or NULL) keeps v_posed (what autograd would save) for
+ * smplb200_smpl_backward; NULL when no vertex gradient will be requested. */
 int smplb200_smpl_forward(const smplb200_model* model, int batch, int rotmat_mode,
                           const float* pose, const float* betas,
-                          float* vertices /*[B][6890][3] or NULL*/, float* joints /*[B][49][3]*/, float* saved_vposed,
+                          float* vertices /*[B][6890][3] or NULL*/, float* joints /*[B][49][3]*/,
+                          float* saved_vposed /*[B][SMPLB200_VPOSED_PITCH] or NULL*/,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Gradient of the above w.r.t. pose (same layout as the input) and betas, given upstream

@@ -2,7 +2,7 @@
 """BASELINE.json config 5: SMPL LBS forward + backward throughput sweep (axis-angle mode, upstream
 gradients dverts ~ N(0,1), djoints ~ N(0,1)), batch 1K..64K, against the HBM and tensor-pipe rooflines.
 
-    python tools/bench_lbs.py [--batches 1024,4096,...] [--reps 5] [--json out.json] [--no-tc]
+    python tools/bench_lbs.py [--batches 1024,4096,...] [--reps 5] [--json out.json]
 
 Every number is CUDA-event time around the C-ABI calls smplb200_smpl_forward / smplb200_smpl_backward
 (inputs resident in HBM, L2 flushed between timed calls).  Algorithmic work per sample:
@@ -52,10 +52,7 @@ def main():
     ap.add_argument('--batches', default='1024,2048,4096,8192,16384,32768,65536')
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--json', default=None)
-    ap.add_argument('--no-tc', action='store_true', help='CUDA-core vertex kernel instead of the tcgen05 one')
     a = ap.parse_args()
-    if a.no_tc:
-        os.environ['SMPLB200_DISABLE_TCGEN05'] = '1'
     dev = torch.device('cuda', 0)
     lib = _native.lib()
     smpl = SMPL(model_arrays=synthetic.model_arrays(0), j_regressor_extra=synthetic.make_extra_regressor(1)).to(dev)
@@ -69,7 +66,7 @@ def main():
         pose = (0.2 * torch.randn(B, 72, generator=g)).to(dev)
         betas = (0.5 * torch.randn(B, 10, generator=g)).to(dev)
         verts = torch.empty(B, 6890, 3, device=dev)
-        vposed = torch.empty(B, 6890, 3, device=dev)
+        vposed = torch.empty(B, _native.VPOSED_PITCH, device=dev)
         joints = torch.empty(B, 49, 3, device=dev)
         dverts = torch.randn(B, 6890, 3, device=dev)
         djoints = torch.randn(B, 49, 3, device=dev)
@@ -112,7 +109,7 @@ def main():
                row['fwd_bwd_alg_tflops']), flush=True)
         del verts, vposed, dverts, ws
         torch.cuda.empty_cache()
-    out = {'workload': 'SMPL LBS fwd+bwd sweep (config 5)', 'vertex_kernel': 'cuda-core' if a.no_tc else 'tcgen05 3xTF32',
+    out = {'workload': 'SMPL LBS fwd+bwd sweep (config 5)', 'vertex_kernels': 'tcgen05 3xTF32 (blend GEMM, skinning, dx GEMM, dA GEMM)',
            'hbm_peak_gbs': hbm, 'bf16_peak_tflops': bf16, 'peak_source': src, 'rows': rows}
     if a.json:
         with open(a.json, 'w') as f:
