@@ -266,7 +266,7 @@ struct SkinBars {
 template <int MODE>
 __global__ void __launch_bounds__(384, 1)
 tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ in, float* __restrict__ out0, float* __restrict__ out1,
-               int batch, int groups) {
+               float* __restrict__ out2, int batch, int groups) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     SkinBars* bars = reinterpret_cast<SkinBars*>(smem + SK_OFF_BAR);
@@ -383,6 +383,8 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
                         if (b < batch) {                                 // padded vertices get zeros (dverts masked above)
                             float* oh = out0 + (size_t)b * kVpPitch + 3 * v;
                             float* ol = out1 + (size_t)b * kVpPitch + 3 * v;
+                            float* oc = out2 + (size_t)b * kVpPitch + 3 * v;     // 16-byte aligned copy of dverts for the dA kernel's TMA
+                            oc[0] = a0; oc[1] = a1; oc[2] = a2;
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) {
                                 const float d = Tt[cc] * a0 + Tt[4 + cc] * a1 + Tt[8 + cc] * a2;
@@ -411,25 +413,37 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
 // =====================================================================================================================
 // dA GEMM with operands generated on chip:  D_e[b, j] = sum_v P_e[b, v] W[v, j],  P_(r,c)[b, v] = dverts[b,v,r] [vp[b,v]; 1][c]
 // (M = 128 samples, N = 24 joints padded to 32, K = the split's vertex range in k-blocks of 32; 12 accumulators of 32
-// columns).  Generator warps read dverts / v_posed rows, form the 12 product tiles of a k-block, split them into hi / lo
-// and store them in the swizzled UMMA layout; the MMA warp consumes them through a 4-stage ring.
+// columns).  The TMA producer streams the k-block's dverts / v_posed tiles ([128 samples][96 coordinates], from the
+// padded 16-byte aligned copies) through a two-stage ring; generator warps read one row-half each (thread = TMEM lane
+// = sample row, 16 of the 32 vertices), form the 12 product tiles, split them into hi / lo and store them straight into
+// TENSOR MEMORY, from where the MMA reads its A operand (tcgen05.mma with A in TMEM): no shared-memory round trip and
+// no operand-fetch bottleneck for the narrow N = 32 MMAs.
+// TMEM columns: 0..383 accumulators, 384..511 two P stages of (hi 32 | lo 32) columns.
 // =====================================================================================================================
-struct alignas(64) DaMaps { CUtensorMap wT_hi, wT_lo; };
-constexpr int DA_PSTAGES = 4, DA_WSTAGES = 2;
-constexpr uint32_t DA_P_STAGE = 2 * TILE128;                   // P_hi | P_lo
+struct alignas(64) DaMaps { CUtensorMap wT_hi, wT_lo, dv, vp; };
+constexpr int DA_PSTAGES = 2, DA_WSTAGES = 2, DA_ISTAGES = 2;
+constexpr int DA_P_COL = 384;                                  // first TMEM column of the P stages
 constexpr uint32_t DA_W_TILE = 32 * BK * 4;                    // 4096
-constexpr uint32_t DA_OFF_W = DA_PSTAGES * DA_P_STAGE;         // 131072
+constexpr uint32_t DA_IN_STAGE = 6 * TILE128;                  // dverts: 3 column blocks of [128 x 32] | v_posed: 3 blocks
+constexpr uint32_t DA_OFF_IN = 0;
+constexpr uint32_t DA_OFF_W = DA_ISTAGES * DA_IN_STAGE;        // 196608
 constexpr uint32_t DA_OFF_BAR = DA_OFF_W + DA_WSTAGES * 2 * DA_W_TILE;
 constexpr uint32_t DA_SMEM = DA_OFF_BAR + 256 + 1024;
+static_assert(DA_SMEM <= 232448, "shared memory budget");
 constexpr int DA_KBLOCKS = kTcVertRowsPad / BK;                // 216
 struct DaBars {
-    uint64_t wfull[DA_WSTAGES], wempty[DA_WSTAGES], pfull[DA_PSTAGES], pempty[DA_PSTAGES], acc_full;
+    uint64_t wfull[DA_WSTAGES], wempty[DA_WSTAGES], ifull[DA_ISTAGES], iempty[DA_ISTAGES], pfull[DA_PSTAGES], pempty[DA_PSTAGES], acc_full;
     uint32_t tmem_base;
 };
 
+// hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 container), lo = x - hi (exact)
+__device__ __forceinline__ void split_trunc(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
 __global__ void __launch_bounds__(384, 1)
-tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dverts, const float* __restrict__ vposed,
-             float* __restrict__ dA_part, int batch, int nsplit) {
+tc_dA_kernel(const __grid_constant__ DaMaps maps, float* __restrict__ dA_part, int batch, int nsplit) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     DaBars* bars = reinterpret_cast<DaBars*>(smem + DA_OFF_BAR);
@@ -440,10 +454,11 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < DA_WSTAGES; ++i) { mbar_init(smem_u32(&bars->wfull[i]), 1); mbar_init(smem_u32(&bars->wempty[i]), 1); }
+        for (int i = 0; i < DA_ISTAGES; ++i) { mbar_init(smem_u32(&bars->ifull[i]), 1); mbar_init(smem_u32(&bars->iempty[i]), 8); }
         for (int i = 0; i < DA_PSTAGES; ++i) { mbar_init(smem_u32(&bars->pfull[i]), 8); mbar_init(smem_u32(&bars->pempty[i]), 1); }
         mbar_init(smem_u32(&bars->acc_full), 1);
         fence_barrier_init();
-        prefetch_tmap(&maps.wT_hi); prefetch_tmap(&maps.wT_lo);
+        prefetch_tmap(&maps.wT_hi); prefetch_tmap(&maps.wT_lo); prefetch_tmap(&maps.dv); prefetch_tmap(&maps.vp);
     }
     if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
     tc_fence_before();
@@ -452,19 +467,32 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
+        // ================= TMA producer: W^T tiles and the dverts / v_posed tiles of every k-block =================
         if (lane == 0) {
-            Ring<DA_WSTAGES> r;
+            Ring<DA_WSTAGES> wr;
+            Ring<DA_ISTAGES> ir;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(smem_u32(&bars->wempty[r.stage]), r.phase ^ 1);
-                const uint32_t full = smem_u32(&bars->wfull[r.stage]);
-                const uint32_t base = s_base + DA_OFF_W + r.stage * 2 * DA_W_TILE;
-                mbar_expect_tx(full, 2 * DA_W_TILE);
-                tma_load_2d(base, &maps.wT_hi, full, kb * BK, 0);
-                tma_load_2d(base + DA_W_TILE, &maps.wT_lo, full, kb * BK, 0);
-                r.advance();
+                mbar_wait(smem_u32(&bars->iempty[ir.stage]), ir.phase ^ 1);
+                const uint32_t ifull = smem_u32(&bars->ifull[ir.stage]);
+                const uint32_t ibase = s_base + DA_OFF_IN + ir.stage * DA_IN_STAGE;
+                mbar_expect_tx(ifull, DA_IN_STAGE);
+#pragma unroll
+                for (int cb = 0; cb < 3; ++cb) {
+                    tma_load_2d(ibase + cb * TILE128, &maps.dv, ifull, (3 * kb + cb) * BK, st * BM);
+                    tma_load_2d(ibase + (3 + cb) * TILE128, &maps.vp, ifull, (3 * kb + cb) * BK, st * BM);
+                }
+                ir.advance();
+                mbar_wait(smem_u32(&bars->wempty[wr.stage]), wr.phase ^ 1);
+                const uint32_t wfull = smem_u32(&bars->wfull[wr.stage]);
+                const uint32_t wbase = s_base + DA_OFF_W + wr.stage * 2 * DA_W_TILE;
+                mbar_expect_tx(wfull, 2 * DA_W_TILE);
+                tma_load_2d(wbase, &maps.wT_hi, wfull, kb * BK, 0);
+                tma_load_2d(wbase + DA_W_TILE, &maps.wT_lo, wfull, kb * BK, 0);
+                wr.advance();
             }
         }
     } else if (warp == 1) {
+        // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = instr_desc(BM, 32);
             Ring<DA_WSTAGES> wr;
@@ -474,19 +502,22 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
                 tc_fence_after();
                 const uint32_t wbase = s_base + DA_OFF_W + wr.stage * 2 * DA_W_TILE;
                 const uint64_t d_wh = smem_desc(wbase), d_wl = smem_desc(wbase + DA_W_TILE);
+                const uint32_t first = (kb != kb0) ? 1u : 0u;
 #pragma unroll 1
                 for (int e = 0; e < 12; ++e) {
                     mbar_wait(smem_u32(&bars->pfull[pr.stage]), pr.phase);
                     tc_fence_after();
-                    const uint32_t pbase = s_base + pr.stage * DA_P_STAGE;
-                    const uint64_t d_ph = smem_desc(pbase), d_pl = smem_desc(pbase + TILE128);
+                    const uint32_t t_ph = tmem_base + DA_P_COL + pr.stage * 64, t_pl = t_ph + 32;
                     const uint32_t tm = tmem_base + e * 32;
+                    umma_tf32_ts(tm, t_ph, d_wh, idesc, first);
+                    umma_tf32_ts(tm, t_pl, d_wh, idesc, 1);
+                    umma_tf32_ts(tm, t_ph, d_wl, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
+                    for (int k = 1; k < BK / 8; ++k) {
                         const uint64_t ko = (uint64_t)(k * 2);
-                        umma_tf32(tm, d_ph + ko, d_wh + ko, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-                        umma_tf32(tm, d_pl + ko, d_wh + ko, idesc, 1);
-                        umma_tf32(tm, d_ph + ko, d_wl + ko, idesc, 1);
+                        umma_tf32_ts(tm, t_ph + 8 * k, d_wh + ko, idesc, 1);
+                        umma_tf32_ts(tm, t_pl + 8 * k, d_wh + ko, idesc, 1);
+                        umma_tf32_ts(tm, t_ph + 8 * k, d_wl + ko, idesc, 1);
                     }
                     umma_commit(smem_u32(&bars->pempty[pr.stage]));
                     pr.advance();
@@ -497,32 +528,29 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
             umma_commit(smem_u32(&bars->acc_full));
         }
     } else if (warp >= 4) {
-        // ================= operand generators (8 warps): thread = (sample row, half of the k-block's 32 vertices) =================
-        const int gt = threadIdx.x - 128;
-        const int rowl = gt & 127, h = gt >> 7;
-        const int b = st * BM + rowl;
-        const bool bok = b < batch;
-        float* ring = reinterpret_cast<float*>(smem);
+        // ================= operand generators (8 warps): thread = (sample row = TMEM lane, half of the k-block's 32 vertices) ======
+        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int rowl = q * 32 + lane;
+        const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         Ring<DA_PSTAGES> pr;
+        Ring<DA_ISTAGES> ir;
         for (int kb = kb0; kb < kb1; ++kb) {
-            const int col0 = 3 * (kb * BK + h * 16);                    // first coordinate column of this thread's 16 vertices
             float dv[48], vp[48];
+            mbar_wait(smem_u32(&bars->ifull[ir.stage]), ir.phase);
             {
-                const float2* pd = reinterpret_cast<const float2*>(dverts + (size_t)b * kCols + col0);
-                const float4* pv = reinterpret_cast<const float4*>(vposed + (size_t)b * kVpPitch + col0);
+                const float* tile = reinterpret_cast<const float*>(smem + DA_OFF_IN + ir.stage * DA_IN_STAGE);
 #pragma unroll
-                for (int i = 0; i < 24; ++i) {
-                    float2 t = make_float2(0.f, 0.f);
-                    if (bok && col0 + 2 * i + 1 < kCols) t = __ldg(pd + i);
-                    dv[2 * i] = t.x; dv[2 * i + 1] = t.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 12; ++i) {
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (bok) t = __ldg(pv + i);
-                    vp[4 * i] = t.x; vp[4 * i + 1] = t.y; vp[4 * i + 2] = t.z; vp[4 * i + 3] = t.w;
+                for (int i = 0; i < 12; ++i) {                       // this thread's 48 coordinates = 12 16-byte chunks of the 96-column row
+                    const int ch = 12 * h + i, cb = ch >> 3, cc = ch & 7;
+                    const float4 a = *reinterpret_cast<const float4*>(tile + cb * (TILE128 / 4) + swz128(rowl, cc));
+                    const float4 c = *reinterpret_cast<const float4*>(tile + (3 + cb) * (TILE128 / 4) + swz128(rowl, cc));
+                    dv[4 * i] = a.x; dv[4 * i + 1] = a.y; dv[4 * i + 2] = a.z; dv[4 * i + 3] = a.w;
+                    vp[4 * i] = c.x; vp[4 * i + 1] = c.y; vp[4 * i + 2] = c.z; vp[4 * i + 3] = c.w;
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->iempty[ir.stage]));       // the row-halves are in registers: refill the stage
+            ir.advance();
 #pragma unroll
             for (int e = 0; e < 12; ++e) {
                 const int r = e >> 2, c = e & 3;
@@ -530,19 +558,15 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float p = (c < 3) ? dv[3 * i + r] * vp[3 * i + c] : dv[3 * i + r];
-                    hi[i] = tf32_round(p);
-                    lo[i] = p - hi[i];
+                    split_trunc(p, hi[i], lo[i]);
                 }
                 mbar_wait(smem_u32(&bars->pempty[pr.stage]), pr.phase ^ 1);
-                float* ph = ring + pr.stage * (DA_P_STAGE / 4);
-                float* pl = ph + TILE128 / 4;
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const uint32_t o = swz128(rowl, 4 * h + qq);
-                    *reinterpret_cast<float4*>(ph + o) = make_float4(hi[4 * qq], hi[4 * qq + 1], hi[4 * qq + 2], hi[4 * qq + 3]);
-                    *reinterpret_cast<float4*>(pl + o) = make_float4(lo[4 * qq], lo[4 * qq + 1], lo[4 * qq + 2], lo[4 * qq + 3]);
-                }
-                fence_proxy_async();
+                tc_fence_after();
+                const uint32_t ta = tmem_base + lane_bits + DA_P_COL + pr.stage * 64 + 16 * h;
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 32, lo);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->pfull[pr.stage]));
                 pr.advance();
@@ -550,11 +574,9 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, const float* __restrict__ dver
         }
         // ================= epilogue (warps 4..7): D_e[b][0..23] -> dA_part[split][b][e][24] =================
         if (warp < 8) {
-            const int q = warp & 3;
-            const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
             mbar_wait(smem_u32(&bars->acc_full), 0);
             tc_fence_after();
-            const int bb = st * BM + q * 32 + lane;
+            const int bb = st * BM + rowl;
 #pragma unroll 1
             for (int e = 0; e < 12; ++e) {
                 float v[32];
@@ -655,12 +677,18 @@ cudaError_t launch_blend_gemm(const TcConstMaps& cm, const float* x_hi, const fl
     return cudaGetLastError();
 }
 
+// K splits of the dx GEMM: the smallest count whose CTA grid fills whole waves of SMs to >= 90 % (else the best one)
 int tc_dx_splits(int batch) {
-    const int mtiles = (batch + tc::BM - 1) / tc::BM;
-    int n = (sm_count() + mtiles - 1) / mtiles;
-    if (n < 1) n = 1;
-    if (n > kMaxSplitX) n = kMaxSplitX;
-    return n;
+    const int mtiles = (batch + tc::BM - 1) / tc::BM, sms = sm_count();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ns = 1; ns <= kMaxSplitX; ++ns) {
+        const int ctas = mtiles * ns, waves = (ctas + sms - 1) / sms;
+        const double eff = (double)ctas / ((double)waves * sms);
+        if (eff >= 0.9) return ns;
+        if (eff > best_eff) { best_eff = eff; best = ns; }
+    }
+    return best;
 }
 
 cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const float* dvp_lo, float* dx_part, int batch, int nsplit,
@@ -687,7 +715,7 @@ cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const flo
 }
 
 static cudaError_t launch_skin(int mode, const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* in, float* out0,
-                               float* out1, int batch, cudaStream_t stream) {
+                               float* out1, float* out2, int batch, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     tc::SkinMaps maps;
     maps.w_hi = cm.w_hi;
@@ -701,18 +729,18 @@ static cudaError_t launch_skin(int mode, const TcConstMaps& cm, const float* ae_
     cudaError_t e = mode == 0 ? opt_in(tc::tc_skin_kernel<0>, tc::SK_SMEM) : opt_in(tc::tc_skin_kernel<1>, tc::SK_SMEM);
     if (e != cudaSuccess) return e;
     const int grid = tc::SK_VBLOCKS * groups;
-    if (mode == 0) tc::tc_skin_kernel<0><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, batch, groups);
-    else tc::tc_skin_kernel<1><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, batch, groups);
+    if (mode == 0) tc::tc_skin_kernel<0><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, out2, batch, groups);
+    else tc::tc_skin_kernel<1><<<grid, 384, tc::SK_SMEM, stream>>>(maps, in, out0, out1, out2, batch, groups);
     return cudaGetLastError();
 }
 
 cudaError_t launch_skin_forward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* vposed, float* verts,
                                 int batch, cudaStream_t stream) {
-    return launch_skin(0, cm, ae_hi, ae_lo, vposed, verts, nullptr, batch, stream);
+    return launch_skin(0, cm, ae_hi, ae_lo, vposed, verts, nullptr, nullptr, batch, stream);
 }
 cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp_hi,
-                                 float* dvp_lo, int batch, cudaStream_t stream) {
-    return launch_skin(1, cm, ae_hi, ae_lo, dverts, dvp_hi, dvp_lo, batch, stream);
+                                 float* dvp_lo, float* dverts_padded, int batch, cudaStream_t stream) {
+    return launch_skin(1, cm, ae_hi, ae_lo, dverts, dvp_hi, dvp_lo, dverts_padded, batch, stream);
 }
 
 int tc_dA_splits(int batch) {
@@ -723,16 +751,18 @@ int tc_dA_splits(int batch) {
     return n;
 }
 
-cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts, const float* vposed, float* dA_part, int batch, int nsplit,
+cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts_padded, const float* vposed, float* dA_part, int batch, int nsplit,
                       cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     tc::DaMaps maps;
     maps.wT_hi = cm.wT_hi;
     maps.wT_lo = cm.wT_lo;
+    if (!make_map(&maps.dv, dverts_padded, kVpPitch, (uint64_t)batch, 0, tc::BM) || !make_map(&maps.vp, vposed, kVpPitch, (uint64_t)batch, 0, tc::BM))
+        return cudaErrorInvalidValue;
     cudaError_t e = opt_in(tc::tc_dA_kernel, tc::DA_SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid(nsplit, (batch + tc::BM - 1) / tc::BM);
-    tc::tc_dA_kernel<<<grid, 384, tc::DA_SMEM, stream>>>(maps, dverts, vposed, dA_part, batch, nsplit);
+    tc::tc_dA_kernel<<<grid, 384, tc::DA_SMEM, stream>>>(maps, dA_part, batch, nsplit);
     return cudaGetLastError();
 }
 

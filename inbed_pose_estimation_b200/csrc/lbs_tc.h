@@ -11,7 +11,7 @@ constexpr int kTcVertRowsPad = 6912;        // 54 vertex blocks x 128 = 216 k-bl
 constexpr int kVpPitch = kColsPad;          // row pitch (floats) of the v_posed / dvp buffers: 20736, 16-byte aligned rows
 constexpr int kAeRow = 12 * 32;             // floats per sample of the skinning-transform operand: [12 entries][24 joints + 8 pad]
 constexpr int kMaxSplitA = 32;              // vertex-range splits of the dA kernel (bounds the tensor-core accumulation chains)
-constexpr int kMaxSplitX = 8;               // K splits of the dx GEMM
+constexpr int kMaxSplitX = 16;              // K splits of the dx GEMM
 
 struct alignas(64) TcConstMaps {  // TMA tensor maps of the immutable model operands (hi / lo tf32 parts)
     CUtensorMap bT_hi, bT_lo;     // basis^T [20736][224]  box 256 x 32   B operand of the blend-shape GEMM
@@ -35,14 +35,15 @@ cudaError_t launch_blend_gemm(const TcConstMaps& cm, const float* x_hi, const fl
 // verts[b][v] = (W . A_b)[v] [v_posed[b][v]; 1]      (tcgen05 skinning GEMM, M = vertices, N = (sample, entry), K = 24)
 cudaError_t launch_skin_forward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* vposed, float* verts,
                                 int batch, cudaStream_t stream);
-// dvp[b][v] = (W . A_b)[v]^R^T dverts[b][v], written as hi / lo tf32 parts [B][20736]
+// dvp[b][v] = (W . A_b)[v]^R^T dverts[b][v], written as hi / lo tf32 parts [B][20736]; also copies dverts into the padded,
+// 16-byte aligned layout [B][20736] the dA kernel's TMA loads need (the caller's [B][6890][3] rows are only 8-byte aligned)
 cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp_hi,
-                                 float* dvp_lo, int batch, cudaStream_t stream);
+                                 float* dvp_lo, float* dverts_padded, int batch, cudaStream_t stream);
 // dx_part[split][B][224] = dvp . basis^T over the split's K range   (tcgen05, K = 20736 split nsplit ways)
 cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const float* dvp_lo, float* dx_part, int batch, int nsplit,
                            cudaStream_t stream);
 // dA_part[split][B][12][24] = sum_v W[v][j] dverts[b][v][r] [v_posed[b][v]; 1][c]   (tcgen05, operands generated on chip)
-cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts, const float* vposed, float* dA_part, int batch, int nsplit,
+cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts_padded, const float* vposed, float* dA_part, int batch, int nsplit,
                       cudaStream_t stream);
 int tc_dA_splits(int batch);
 int tc_dx_splits(int batch);

@@ -1,5 +1,5 @@
-"""Aggregate an ncu report's warp-stall samples per CUDA source line.
-usage: python tools/ncu_lines.py report.ncu-rep [top_n]"""
+"""Aggregate an ncu report's warp-stall samples per CUDA source line (with the top stall reasons of each line).
+usage: python tools/ncu_lines.py report.ncu-rep [top_n] [kernel-name-regex]"""
 import csv
 import subprocess
 import sys
@@ -7,11 +7,13 @@ from collections import defaultdict
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv'],
-                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True).stdout
+cmd = ['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv']
+if len(sys.argv) > 3:
+    cmd += ['--kernel-name', 'regex:' + sys.argv[3]]
+out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = None
-agg = defaultdict(lambda: [0, 0, ''])
+agg = defaultdict(lambda: [0, 0, '', defaultdict(int)])
 hdr = None
 total = 0
 for r in rows:
@@ -24,6 +26,7 @@ for r in rows:
         hdr = r
         i_s = hdr.index('# Samples')
         i_x = hdr.index('Instructions Executed')
+        stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith('stall_') and '(Not Issued)' not in h]
         continue
     if hdr is None or r[0] in ('Function Name',):
         continue
@@ -35,32 +38,14 @@ for r in rows:
         key = (cur_file, int(r[0]))
         agg[key][0] += s
         agg[key][1] += x
-        agg[key][2] = r[1].strip()[:110]
+        agg[key][2] = r[1].strip()[:90]
+        for i, name in stall_cols:
+            try:
+                agg[key][3][name] += int(r[i])
+            except ValueError:
+                pass
         total += s
 print('total samples', total)
-for (f, ln), (s, x, src) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    print('%5.1f%% %9d inst  %s:%d  %s' % (100.0 * s / max(total, 1), x, f, ln, src))
-
-# ---- aggregate per enclosing function (by line ranges of "SB_HD ... name(" definitions) ----
-import os, re
-root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'inbed_pose_estimation_b200', 'csrc')
-funcs = {}
-for fn in os.listdir(root):
-    if not fn.endswith(('.cuh', '.cu', '.h')):
-        continue
-    starts = []
-    for i, line in enumerate(open(os.path.join(root, fn)), 1):
-        m = re.match(r'^(?:SB_HD|__global__|static|template|inline|cudaError_t)?.*?\b([A-Za-z_0-9]+)\s*\((?:const|float|int|bool|ModelView|FitParams|PoseParams)', line)
-        if m and not line.startswith((' ', '\t', '//', '#')) and '(' in line and ';' not in line:
-            starts.append((i, m.group(1)))
-    funcs[fn] = starts
-per = defaultdict(int)
-for (f, ln), (s, x, src) in agg.items():
-    name = '?'
-    for st, nm in funcs.get(f, []):
-        if st <= ln:
-            name = nm
-    per[(f, name)] += s
-print('\nper function:')
-for (f, name), s in sorted(per.items(), key=lambda kv: -kv[1])[:25]:
-    print('%5.1f%%  %s:%s' % (100.0 * s / max(total, 1), f, name))
+for (f, ln), (s, x, src, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    tops = ' '.join('%s=%d%%' % (n, 100 * v // max(s, 1)) for n, v in sorted(st.items(), key=lambda kv: -kv[1])[:3] if v)
+    print('%5.1f%% %10d inst  %s:%d  %s   [%s]' % (100.0 * s / max(total, 1), x, f, ln, src, tops))
