@@ -123,25 +123,25 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(BM, NT);
-            Ring<STAGES> r;
-            Ring<2> t;
-            for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {
-                int mt, nt, sp, kb0, kb1;
-                decode(item, mt, nt, sp, kb0, kb1);
-                for (int g0 = kb0; g0 < kb1; g0 += work.chain) {
-                    const int g1 = (g0 + work.chain < kb1) ? g0 + work.chain : kb1;
-                    mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);       // consumers drained this accumulator
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+        constexpr uint32_t idesc = instr_desc(BM, NT);
+        Ring<STAGES> r;
+        Ring<2> t;
+        for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {
+            int mt, nt, sp, kb0, kb1;
+            decode(item, mt, nt, sp, kb0, kb1);
+            for (int g0 = kb0; g0 < kb1; g0 += work.chain) {
+                const int g1 = (g0 + work.chain < kb1) ? g0 + work.chain : kb1;
+                mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);       // consumers drained this accumulator
+                tc_fence_after();
+                const uint32_t tm = tmem_base + t.stage * NT;
+                for (int kb = g0; kb < g1; ++kb) {
+                    mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
                     tc_fence_after();
-                    const uint32_t tm = tmem_base + t.stage * NT;
-                    for (int kb = g0; kb < g1; ++kb) {
-                        mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
-                        tc_fence_after();
-                        const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
-                        const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + TILE128);
-                        const uint64_t d_bh = smem_desc(base + 2 * TILE128), d_bl = smem_desc(base + 2 * TILE128 + SM::B_BYTES);
+                    const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
+                    const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + TILE128);
+                    const uint64_t d_bh = smem_desc(base + 2 * TILE128), d_bl = smem_desc(base + 2 * TILE128 + SM::B_BYTES);
+                    if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / 8; ++k) {
                             const uint64_t ko = (uint64_t)(k * 2);          // 32 bytes per k-step, in 16-byte units
@@ -150,11 +150,13 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
                             umma_tf32(tm, d_ah + ko, d_bl + ko, idesc, 1);
                         }
                         umma_commit(smem_u32(&bars->empty[r.stage]));
-                        r.advance();
                     }
-                    umma_commit(smem_u32(&bars->tmem_full[t.stage]));
-                    t.advance();
+                    __syncwarp();
+                    r.advance();
                 }
+                if (elect_one()) umma_commit(smem_u32(&bars->tmem_full[t.stage]));
+                __syncwarp();
+                t.advance();
             }
         }
     } else if (warp >= 4) {
@@ -306,20 +308,20 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(BM, SK_N);
-            const uint64_t d_wh = smem_desc(s_base), d_wl = smem_desc(s_base + TILE128);
-            mbar_wait(smem_u32(&bars->wfull), 0);
+        constexpr uint32_t idesc = instr_desc(BM, SK_N);
+        const uint64_t d_wh = smem_desc(s_base), d_wl = smem_desc(s_base + TILE128);
+        mbar_wait(smem_u32(&bars->wfull), 0);
+        tc_fence_after();
+        Ring<SK_STAGES> r;
+        Ring<2> t;
+        for (int c = g; c < nchunks; c += groups) {
+            mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);
+            mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
             tc_fence_after();
-            Ring<SK_STAGES> r;
-            Ring<2> t;
-            for (int c = g; c < nchunks; c += groups) {
-                mbar_wait(smem_u32(&bars->tmem_empty[t.stage]), t.phase ^ 1);
-                mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
-                tc_fence_after();
-                const uint32_t base = s_base + SK_OFF_RING + r.stage * SK_STAGE_BYTES;
-                const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + SK_AE_BYTES);
-                const uint32_t tm = tmem_base + t.stage * SK_N;
+            const uint32_t base = s_base + SK_OFF_RING + r.stage * SK_STAGE_BYTES;
+            const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + SK_AE_BYTES);
+            const uint32_t tm = tmem_base + t.stage * SK_N;
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {                 // 24 joints = 3 k-steps of 8
                     const uint64_t ko = (uint64_t)(k * 2);
@@ -329,9 +331,10 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
                 }
                 umma_commit(smem_u32(&bars->empty[r.stage]));
                 umma_commit(smem_u32(&bars->tmem_full[t.stage]));
-                r.advance();
-                t.advance();
             }
+            __syncwarp();
+            r.advance();
+            t.advance();
         }
     } else if (warp >= 4) {
         const int q = warp & 3, half = (warp - 4) >> 2;
@@ -492,23 +495,23 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, float* __restrict__ dA_part, i
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc(BM, 32);
-            Ring<DA_WSTAGES> wr;
-            Ring<DA_PSTAGES> pr;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(smem_u32(&bars->wfull[wr.stage]), wr.phase);
-                tc_fence_after();
-                const uint32_t wbase = s_base + DA_OFF_W + wr.stage * 2 * DA_W_TILE;
-                const uint64_t d_wh = smem_desc(wbase), d_wl = smem_desc(wbase + DA_W_TILE);
-                const uint32_t first = (kb != kb0) ? 1u : 0u;
+        // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
+        constexpr uint32_t idesc = instr_desc(BM, 32);
+        Ring<DA_WSTAGES> wr;
+        Ring<DA_PSTAGES> pr;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(smem_u32(&bars->wfull[wr.stage]), wr.phase);
+            tc_fence_after();
+            const uint32_t wbase = s_base + DA_OFF_W + wr.stage * 2 * DA_W_TILE;
+            const uint64_t d_wh = smem_desc(wbase), d_wl = smem_desc(wbase + DA_W_TILE);
+            const uint32_t first = (kb != kb0) ? 1u : 0u;
 #pragma unroll 1
-                for (int e = 0; e < 12; ++e) {
-                    mbar_wait(smem_u32(&bars->pfull[pr.stage]), pr.phase);
-                    tc_fence_after();
-                    const uint32_t t_ph = tmem_base + DA_P_COL + pr.stage * 64, t_pl = t_ph + 32;
-                    const uint32_t tm = tmem_base + e * 32;
+            for (int e = 0; e < 12; ++e) {
+                mbar_wait(smem_u32(&bars->pfull[pr.stage]), pr.phase);
+                tc_fence_after();
+                const uint32_t t_ph = tmem_base + DA_P_COL + pr.stage * 64, t_pl = t_ph + 32;
+                const uint32_t tm = tmem_base + e * 32;
+                if (elect_one()) {
                     umma_tf32_ts(tm, t_ph, d_wh, idesc, first);
                     umma_tf32_ts(tm, t_pl, d_wh, idesc, 1);
                     umma_tf32_ts(tm, t_ph, d_wl, idesc, 1);
@@ -520,13 +523,16 @@ tc_dA_kernel(const __grid_constant__ DaMaps maps, float* __restrict__ dA_part, i
                         umma_tf32_ts(tm, t_ph + 8 * k, d_wl + ko, idesc, 1);
                     }
                     umma_commit(smem_u32(&bars->pempty[pr.stage]));
-                    pr.advance();
                 }
-                umma_commit(smem_u32(&bars->wempty[wr.stage]));
-                wr.advance();
+                __syncwarp();
+                pr.advance();
             }
-            umma_commit(smem_u32(&bars->acc_full));
+            if (elect_one()) umma_commit(smem_u32(&bars->wempty[wr.stage]));
+            __syncwarp();
+            wr.advance();
         }
+        if (elect_one()) umma_commit(smem_u32(&bars->acc_full));
+        __syncwarp();
     } else if (warp >= 4) {
         // ================= operand generators (8 warps): thread = (sample row = TMEM lane, half of the k-block's 32 vertices) ======
         const int q = warp & 3, h = (warp - 4) >> 2;

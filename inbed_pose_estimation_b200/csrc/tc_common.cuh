@@ -154,6 +154,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
 }
 
+// One lane of a converged warp.  MMA / TMA issue loops run warp-uniform (all lanes wait on the barriers and compute the
+// descriptors, so the compiler keeps them in uniform registers) and only the issue itself is predicated on the elected
+// lane; issuing from inside an `if (lane == 0)` region costs a register -> uniform-register round trip per instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ring position: stage index + phase bit
 template <int STAGES>
 struct Ring {
