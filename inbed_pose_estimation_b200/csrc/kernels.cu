@@ -78,22 +78,30 @@ cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stre
     return launch_fit_variant<4, kFitThreads, 1>(M, P, stream);
 }
 
-cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
-    if (P.batch <= 0) return cudaSuccess;
-    constexpr int S = 8;
+template <int S>
+static cudaError_t launch_pose_forward_s(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
     cudaError_t e = opt_in_smem(pose_forward_kernel<S>, tile_smem_bytes<S>());
     if (e != cudaSuccess) return e;
     pose_forward_kernel<S><<<(P.batch + S - 1) / S, kPoseThreads, tile_smem_bytes<S>(), stream>>>(M, P);
     return cudaGetLastError();
 }
-
-cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
-    if (P.batch <= 0) return cudaSuccess;
-    constexpr int S = 8;
+template <int S>
+static cudaError_t launch_pose_backward_s(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
     cudaError_t e = opt_in_smem(pose_backward_kernel<S>, tile_smem_bytes<S>());
     if (e != cudaSuccess) return e;
     pose_backward_kernel<S><<<(P.batch + S - 1) / S, kPoseThreads, tile_smem_bytes<S>(), stream>>>(M, P);
     return cudaGetLastError();
+}
+
+// 16 samples per CTA halve the folded-basis bytes streamed from L2 per sample; small batches use 8 to fill more SMs.
+cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
+    if (P.batch <= 0) return cudaSuccess;
+    return P.batch >= 16 * 128 ? launch_pose_forward_s<16>(M, P, stream) : launch_pose_forward_s<8>(M, P, stream);
+}
+
+cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaStream_t stream) {
+    if (P.batch <= 0) return cudaSuccess;
+    return P.batch >= 16 * 128 ? launch_pose_backward_s<16>(M, P, stream) : launch_pose_backward_s<8>(M, P, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

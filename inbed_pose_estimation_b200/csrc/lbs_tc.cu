@@ -342,24 +342,35 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
         const bool vok = v < kVerts;
         const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
         Ring<2> t;
-        for (int c = g; c < nchunks; c += groups) {
+        // this thread's inputs of one chunk: 8 samples x 3 coordinates; the next chunk's are fetched before the current
+        // one is transformed (software pipeline: keeps HBM reads in flight while the warp waits on TMEM / stores)
+        auto fetch = [&](int c, float (&dst)[8][3]) {
             const int b0 = c * SK_NB + half * 8;
-            float iv[8][3];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = b0 + i;
                 if (MODE == 0) {
-                    const bool ok = b < batch;                           // pitch covers the padded vertices
+                    const bool ok = c < nchunks && b < batch;            // pitch covers the padded vertices
                     const float* p = in + (size_t)b * kVpPitch + 3 * v;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) iv[i][a] = ok ? __ldg(p + a) : 0.f;
+                    for (int a = 0; a < 3; ++a) dst[i][a] = ok ? __ldg(p + a) : 0.f;
                 } else {
-                    const bool ok = vok && b < batch;
+                    const bool ok = c < nchunks && vok && b < batch;
                     const float* p = in + (size_t)b * kCols + 3 * v;
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) iv[i][a] = ok ? __ldg(p + a) : 0.f;
+                    for (int a = 0; a < 3; ++a) dst[i][a] = ok ? __ldg(p + a) : 0.f;
                 }
             }
+        };
+        float iv[8][3], nx[8][3];
+        fetch(g, nx);
+        for (int c = g; c < nchunks; c += groups) {
+            const int b0 = c * SK_NB + half * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) iv[i][a] = nx[i][a];
+            fetch(c + groups, nx);
             mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_bits + t.stage * SK_N + half * 96;

@@ -1,5 +1,5 @@
 """Aggregate an ncu report's warp-stall samples per CUDA source line (with the top stall reasons of each line).
-usage: python tools/ncu_lines.py report.ncu-rep [top_n] [kernel-name-regex]"""
+usage: python tools/ncu_lines.py report.ncu-rep [top_n] [kernel-name-regex [nth-launch]]"""
 import csv
 import subprocess
 import sys
@@ -8,7 +8,9 @@ from collections import defaultdict
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 cmd = ['ncu', '-i', rep, '--page', 'source', '--print-source', 'cuda,sass', '--csv']
-if len(sys.argv) > 3:
+if len(sys.argv) > 4:                       # Nth launch of the kernels matching the regex
+    cmd += ['--kernel-id', '::regex:%s:%s' % (sys.argv[3], sys.argv[4])]
+elif len(sys.argv) > 3:
     cmd += ['--kernel-name', 'regex:' + sys.argv[3]]
 out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True).stdout
 rows = list(csv.reader(out.splitlines()))
