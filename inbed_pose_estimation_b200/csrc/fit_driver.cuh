@@ -72,15 +72,49 @@ SB_HD SmallConsts stage_small_consts(const ModelView& M, float* sm) {
     return C;
 }
 
+// Kinematic chain + folded forward GEMM (independent of each other: the chain reads the rotations and rest joints, the
+// GEMM reads x).  On the device with the standard 384-thread tile the chain's level sweeps run on warp 11, which no GEMM
+// work item lands on, concurrently with the GEMM; otherwise one after the other.  Ends with a tile barrier.
+template <int S>
+SB_HD void ph_chain_and_gemm_forward(const ModelView& M, float* sm) {
+#if defined(__CUDA_ARCH__)
+    if (S % 8 == 0 && TILE_NT == kFitTileThreads) {
+        if (TILE_TID >= kChainWarpFirstThread) ph_chain_forward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
+        else ph_fold_gemm_forward<S>(M, sm);
+        TILE_SYNC();
+        return;
+    }
+#endif
+    ph_chain_forward<S>(M, sm, grp_tile());           // ends with a barrier
+    ph_fold_gemm_forward<S>(M, sm);
+    TILE_SYNC();
+}
+
+// Folded backward GEMM + reverse chain sweep, overlapped the same way (the sweep needs dL/dG from ph_joint_backward only;
+// the GEMM's dL/dx is added to dL/dR afterwards in rotation_grad).  Ends with a tile barrier.
+template <int S>
+SB_HD void ph_gemm_and_chain_backward(const ModelView& M, float* sm) {
+#if defined(__CUDA_ARCH__)
+    if (S % 8 == 0 && TILE_NT == kFitTileThreads) {
+        if (TILE_TID >= kChainWarpFirstThread) ph_chain_backward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
+        ph_fold_gemm_backward<S>(M, sm);              // warp 11 owns no GEMM range: it only joins the barriers and the combine
+        TILE_SYNC();
+        return;
+    }
+#endif
+    ph_fold_gemm_backward<S>(M, sm);
+    TILE_SYNC();
+    ph_chain_backward<S>(M, sm, grp_tile());
+    TILE_SYNC();
+}
+
 // forward through the folded joint model for the tile's current parameters
 template <int S>
 SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, bool from_axis_angle, bool root_identity) {
     ph_pose_features<S>(sm, from_axis_angle, root_identity);
     ph_rest_joints<S>(C, sm);
     TILE_SYNC();
-    ph_chain_forward<S>(M, sm);           // ends with a barrier
-    ph_fold_gemm_forward<S>(M, sm);
-    TILE_SYNC();
+    ph_chain_and_gemm_forward<S>(M, sm);
     ph_output_joints<S>(M, C, sm);
     TILE_SYNC();
 }
@@ -257,10 +291,8 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
             ph_rest_joints<S>(C, sm);
             TILE_SYNC();
             PHASE_MARK(2);
-            ph_chain_forward<S>(M, sm);           // ends with a barrier
             PHASE_MARK(3);
-            ph_fold_gemm_forward<S>(M, sm);
-            TILE_SYNC();
+            ph_chain_and_gemm_forward<S>(M, sm);
             PHASE_MARK(4);
             ph_output_joints<S>(M, C, sm);
             TILE_SYNC();
@@ -284,11 +316,8 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
             ph_pick_backward<S>(M, C, sm);
             TILE_SYNC();
             PHASE_MARK(8);
-            ph_fold_gemm_backward<S>(M, sm);
-            TILE_SYNC();
             PHASE_MARK(9);
-            ph_chain_backward<S>(M, sm);
-            TILE_SYNC();
+            ph_gemm_and_chain_backward<S>(M, sm);
             PHASE_MARK(10);
             const AdamScalars sc = adam_tab[it];
             FOR_ITEMS(itj, kJoints * S) {
@@ -422,8 +451,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
     TILE_SYNC();
     ph_pick_backward<S>(M, C, sm);
     TILE_SYNC();
-    ph_fold_gemm_backward<S>(M, sm);
-    TILE_SYNC();
+    ph_gemm_and_chain_backward<S>(M, sm);
     if (P.dx_part) {
         FOR_ITEMS(it, S * kXPad) {
             const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
@@ -435,8 +463,6 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
         }
         TILE_SYNC();
     }
-    ph_chain_backward<S>(M, sm);
-    TILE_SYNC();
     FOR_ITEMS(it, kJoints * S) {
         const int s = it % S, j = it / S, b = tile * S + s;
         float g[9];

@@ -30,6 +30,21 @@ namespace smplb200 {
 #define FOR_ITEMS(it, n) for (int it = TILE_TID; it < (n); it += TILE_NT)
 #define TILE_SYNC_NONE() ((void)0)
 
+// The threads that execute a phase: the whole tile (block barrier between sub-steps) or a single warp (warp barrier).
+// The latency-bound kinematic-chain sweeps run on the one warp the folded GEMMs leave idle, concurrently with them.
+struct Grp { int tid, nt, warp_only; };
+SB_HD Grp grp_tile() { return Grp{TILE_TID, TILE_NT, 0}; }
+SB_HD void grp_sync(const Grp& g) {
+#if defined(__CUDA_ARCH__)
+    if (g.warp_only) __syncwarp();
+    else __syncthreads();
+#else
+    (void)g;
+#endif
+}
+#define FOR_ITEMS_G(it, n, g) for (int it = (g).tid; it < (n); it += (g).nt)
+constexpr int kChainWarpFirstThread = 352;      // warp 11 of a 384-thread tile: no work item of either folded GEMM lands on it
+
 // Small per-model constants every iteration touches; the kernels stage them in shared memory once
 // (global / L2 latency would otherwise be exposed in the short per-sample phases).
 struct SmallConsts {
@@ -211,11 +226,11 @@ SB_HD void ph_rest_joints(const SmallConsts& C, float* sm) {
 
 // World transforms level by level; also A_j^t = G_j^t - G_j^R J_j.
 template <int S>
-SB_HD void ph_chain_forward(const ModelView& M, float* sm) {
+SB_HD void ph_chain_forward(const ModelView& M, float* sm, const Grp g) {
     using L = TileLayout<S>;
     for (int lev = 0; lev < M.num_levels; ++lev) {
         const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
-        FOR_ITEMS(it, cnt * S) {
+        FOR_ITEMS_G(it, cnt * S, g) {
             const int s = it % S, j = M.level_order[first + it / S], p = M.parents[j];
             float G[12];
             const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s],
@@ -249,7 +264,7 @@ SB_HD void ph_chain_forward(const ModelView& M, float* sm) {
             for (int r = 0; r < 3; ++r)
                 sm[L::AT + (3 * j + r) * S + s] = G[r * 4 + 3] - (G[r * 4 + 0] * Jx + G[r * 4 + 1] * Jy + G[r * 4 + 2] * Jz);
         }
-        TILE_SYNC();
+        grp_sync(g);
     }
 }
 
@@ -714,11 +729,11 @@ SB_HD void ph_pick_backward(const ModelView& M, const SmallConsts& C, float* sm)
 // (deterministic, no atomics); then every joint derives dL/dR_j (stored over RM) and the
 // rest-joint gradient DJ.
 template <int S>
-SB_HD void ph_chain_backward(const ModelView& M, float* sm) {
+SB_HD void ph_chain_backward(const ModelView& M, float* sm, const Grp g) {
     using L = TileLayout<S>;
     for (int lev = M.num_levels - 2; lev >= 0; --lev) {
         const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
-        FOR_ITEMS(it, cnt * S) {
+        FOR_ITEMS_G(it, cnt * S, g) {
             const int s = it % S, p = M.level_order[first + it / S];
             const int c0 = M.child_start[p], c1 = M.child_start[p + 1];
             if (c0 == c1) continue;
@@ -758,9 +773,9 @@ SB_HD void ph_chain_backward(const ModelView& M, float* sm) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) sm[L::DJ + (3 * p + c) * S + s] = dJp[c];
         }
-        TILE_SYNC();
+        grp_sync(g);
     }
-    FOR_ITEMS(it, kJoints * S) {
+    FOR_ITEMS_G(it, kJoints * S, g) {
         const int s = it % S, j = it / S, p = M.parents[j];
         float dGi[12];
 #pragma unroll

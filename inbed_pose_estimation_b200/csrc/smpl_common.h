@@ -72,6 +72,7 @@ struct AdamScalars {           // per-iteration host-computed scalars (torch com
     float bc2_sqrt;            // sqrt(1 - beta2^t)
 };
 
+constexpr int kFitTileThreads = 384; // threads of the standard tile (fit and pose kernels)
 constexpr int kMaxIters = 256;     // per stage; bounds the in-kernel Adam scalar table
 
 }  // namespace smplb200
