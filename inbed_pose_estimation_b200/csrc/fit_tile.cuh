@@ -315,6 +315,46 @@ struct Tile4x8 {
 #endif
 };
 
+// acc[c][s] += sum_{k < K} w[k * ldw4][c] * x[k * ldx + s]  for the 4 columns of one float4 column quad and 8 samples:
+// the streamed-constant GEMM core of the three GEMM phases.  The constant rows come from L2 in groups of 4, two groups
+// ahead, through three register sets used in rotation (no register moves in the steady state); the x row of the next
+// k-step is fetched from shared memory while the current one is multiplied.  Measured in isolation on B200
+// (tools/exp/gemm_probe.cu): 70 % of the fp32 FMA peak against 57 % for the plain two-deep prefetch loop.
+template <int K>
+SB_HD void stream_gemm_4x8(Tile4x8& acc, const float4* w, int ldw4, const float* x, int ldx) {
+    constexpr int U = 4, G = K / U;
+    static_assert(K % U == 0 && G >= 2, "K must be a multiple of 4, at least 8");
+    float4 ca[U], cb[U], cc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ca[u] = ld_const4(w + u * ldw4); cb[u] = ld_const4(w + (U + u) * ldw4); cc[u] = cb[u]; }
+    float4 v0 = reinterpret_cast<const float4*>(x)[0], v1 = reinterpret_cast<const float4*>(x)[1];
+    auto step = [&](const float4 (&cur)[U], float4 (&nxt)[U], int g) {
+        if (g + 2 < G) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) nxt[u] = ld_const4(w + ((g + 2) * U + u) * ldw4);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int kn = (g * U + u + 1 < K) ? g * U + u + 1 : g * U + u;      // next row (the last one is re-read, unused)
+            const float4* xr = reinterpret_cast<const float4*>(x + kn * ldx);
+            const float4 n0 = xr[0], n1 = xr[1];
+            acc.fma(cur[u], v0, v1);
+            v0 = n0; v1 = n1;
+        }
+    };
+    constexpr int ROUNDS = (G - 2) / 3, TAIL = G - 3 * ROUNDS;          // TAIL in {2, 3, 4}
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; ++r) {
+        step(ca, cc, 3 * r);
+        step(cb, ca, 3 * r + 1);
+        step(cc, cb, 3 * r + 2);
+    }
+    step(ca, cc, 3 * ROUNDS);
+    step(cb, ca, 3 * ROUNDS + 1);
+    if (TAIL > 2) step(cc, cb, 3 * ROUNDS + 2);
+    if (TAIL > 3) step(ca, cc, 3 * ROUNDS + 3);
+}
+
 // QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
 // S % 8 == 0: one thread owns 4 adjacent columns x 8 samples (32 accumulators, 1 LDG.128 + 2 LDS.128 per
 // 32 FMAs); the basis rows are streamed from L2 two groups of U rows ahead, x is broadcast from smem.
@@ -323,32 +363,12 @@ SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
     if constexpr (S % 8 == 0) {
-        constexpr int U = 4, NQ4 = kQPad / 4, H = S / 8;       // 176 column quads, H sample groups
-        static_assert(kXPad % U == 0, "k padding");
+        constexpr int NQ4 = kQPad / 4, H = S / 8;       // 176 column quads, H sample groups
         FOR_ITEMS(t, NQ4 * H) {
             const int cq = t % NQ4, h = t / NQ4;
             Tile4x8 acc;
             acc.clear();
-            const float4* cf = reinterpret_cast<const float4*>(M.Cf) + cq;
-            const float* xb = sm + L::XT + 8 * h;
-            float4 c0[U], c1[U], c2[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { c0[u] = ld_const4(cf + u * NQ4); c1[u] = ld_const4(cf + (U + u) * NQ4); c2[u] = c1[u]; }
-#pragma unroll 1
-            for (int m0 = 0; m0 < kXPad; m0 += U) {
-                if (m0 + 2 * U < kXPad) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) c2[u] = ld_const4(cf + (m0 + 2 * U + u) * NQ4);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float4* xr = reinterpret_cast<const float4*>(xb + (m0 + u) * S);
-                    const float4 v0 = xr[0], v1 = xr[1];
-                    acc.fma(c0[u], v0, v1);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) { c0[u] = c1[u]; c1[u] = c2[u]; }
-            }
+            stream_gemm_4x8<kXPad>(acc, reinterpret_cast<const float4*>(M.Cf) + cq, NQ4, sm + L::XT + 8 * h, S);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float4* qo = reinterpret_cast<float4*>(sm + L::QT + (4 * cq + c) * L::LDQ + 8 * h);
@@ -381,8 +401,8 @@ SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
 #if defined(__CUDA_ARCH__)
     if constexpr (S % 8 == 0) {
-        constexpr int U = 4, MQ = kXPad / 4, H = S / 8, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
-        static_assert(NR * NPER <= kQPad && NR * NPER >= kQ && NPER % U == 0, "n ranges");
+        constexpr int MQ = kXPad / 4, H = S / 8, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
+        static_assert(NR * NPER <= kQPad && NR * NPER >= kQ && NPER % 4 == 0, "n ranges");
         constexpr int PER_R = MQ * H;                                          // 112 threads per range when S = 16
         if (TILE_NT >= PER_R * NR) {
             const int tid = TILE_TID, r = tid / PER_R, w = tid % PER_R, mq = w % MQ, h = w / MQ;
@@ -391,26 +411,8 @@ SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
             acc.clear();
             if (active) {
                 const int n_begin = r * NPER;
-                const float4* ct = reinterpret_cast<const float4*>(M.CfT) + (size_t)n_begin * MQ + mq;
-                const float* qb = sm + L::QT + n_begin * L::LDQ + 8 * h;
-                float4 c0[U], c1[U], c2[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) { c0[u] = ld_const4(ct + u * MQ); c1[u] = ld_const4(ct + (U + u) * MQ); c2[u] = c1[u]; }
-#pragma unroll 1
-                for (int n0 = 0; n0 < NPER; n0 += U) {
-                    if (n0 + 2 * U < NPER) {
-#pragma unroll
-                        for (int u = 0; u < U; ++u) c2[u] = ld_const4(ct + (n0 + 2 * U + u) * MQ);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float4* qr = reinterpret_cast<const float4*>(qb + (n0 + u) * L::LDQ);
-                        const float4 v0 = qr[0], v1 = qr[1];
-                        acc.fma(c0[u], v0, v1);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) { c0[u] = c1[u]; c1[u] = c2[u]; }
-                }
+                stream_gemm_4x8<NPER>(acc, reinterpret_cast<const float4*>(M.CfT) + (size_t)n_begin * MQ + mq, MQ,
+                                      sm + L::QT + n_begin * L::LDQ + 8 * h, L::LDQ);
             }
             TILE_SYNC();                               // everyone is done reading dQ: QT becomes scratch
             if (active) {
@@ -533,43 +535,66 @@ SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad)
 template <int S>
 SB_HD void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
-    constexpr int U = 8, IP = kPriorPad / 2;        // 36 column pairs per component
-    static_assert(kPriorPad % U == 0, "prior padding");
-    FOR_ITEMS(t, kGauss * IP) {
-        const int g = t / IP, ip = t % IP;
-        float a0[S], a1[S];
+    if constexpr (S % 8 == 0) {
+        // 4 adjacent i x 8 samples per thread through the streamed-constant GEMM core (rows j >= 69 of Psym are zero;
+        // the pose rows they meet - the first betas - are finite)
+        constexpr int IQ = kPriorPad / 4, H = S / 8;        // 18 column quads per component
+        FOR_ITEMS(t, kGauss * IQ * H) {
+            const int h = t / (kGauss * IQ), gi = t % (kGauss * IQ), g = gi / IQ, iq = gi % IQ;
+            Tile4x8 acc;
+            acc.clear();
+            stream_gemm_4x8<kPriorPad>(acc, reinterpret_cast<const float4*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + iq, IQ,
+                                       sm + L::POSE + 3 * S + 8 * h, S);
 #pragma unroll
-        for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
-        const float2* P = reinterpret_cast<const float2*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + ip;
-        float2 cur[U], nxt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { cur[u] = ld_const2(P + u * IP); nxt[u] = cur[u]; }
-#pragma unroll 1
-        for (int j0 = 0; j0 < kPriorPad; j0 += U) {
-            if (j0 + U < kPriorPad) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) nxt[u] = ld_const2(P + (j0 + U + u) * IP);
+            for (int c = 0; c < 4; ++c) {
+                const float pm = C.pmean[g * kPriorPad + 4 * iq + c];
+                float4 lo = acc.lo(c), hi = acc.hi(c);
+                lo.x -= pm; lo.y -= pm; lo.z -= pm; lo.w -= pm;
+                hi.x -= pm; hi.y -= pm; hi.z -= pm; hi.w -= pm;
+                float4* o = reinterpret_cast<float4*>(sm + L::QT + (g * kPriorPad + 4 * iq + c) * S + 8 * h);
+                o[0] = lo;
+                o[1] = hi;
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                // rows j >= 69 of Psym are zero; the pose rows they meet (first betas) are finite
-                const float4* br = reinterpret_cast<const float4*>(sm + L::POSE + (3 + j0 + u) * S);
-#pragma unroll
-                for (int q = 0; q < S / 4; ++q) {
-                    const float4 v = br[q];
-                    a0[4 * q + 0] += cur[u].x * v.x; a0[4 * q + 1] += cur[u].x * v.y;
-                    a0[4 * q + 2] += cur[u].x * v.z; a0[4 * q + 3] += cur[u].x * v.w;
-                    a1[4 * q + 0] += cur[u].y * v.x; a1[4 * q + 1] += cur[u].y * v.y;
-                    a1[4 * q + 2] += cur[u].y * v.z; a1[4 * q + 3] += cur[u].y * v.w;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
         }
-        const float pm0 = C.pmean[g * kPriorPad + 2 * ip], pm1 = C.pmean[g * kPriorPad + 2 * ip + 1];
-        float* o = sm + L::QT + (g * kPriorPad + 2 * ip) * S;
-#pragma unroll
-        for (int s = 0; s < S; ++s) { o[s] = a0[s] - pm0; o[S + s] = a1[s] - pm1; }
+    } else {
+        constexpr int U = 8, IP = kPriorPad / 2;        // 36 column pairs per component
+        static_assert(kPriorPad % U == 0, "prior padding");
+        FOR_ITEMS(t, kGauss * IP) {
+            const int g = t / IP, ip = t % IP;
+            float a0[S], a1[S];
+    #pragma unroll
+            for (int s = 0; s < S; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+            const float2* P = reinterpret_cast<const float2*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + ip;
+            float2 cur[U], nxt[U];
+    #pragma unroll
+            for (int u = 0; u < U; ++u) { cur[u] = ld_const2(P + u * IP); nxt[u] = cur[u]; }
+    #pragma unroll 1
+            for (int j0 = 0; j0 < kPriorPad; j0 += U) {
+                if (j0 + U < kPriorPad) {
+    #pragma unroll
+                    for (int u = 0; u < U; ++u) nxt[u] = ld_const2(P + (j0 + U + u) * IP);
+                }
+    #pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    // rows j >= 69 of Psym are zero; the pose rows they meet (first betas) are finite
+                    const float4* br = reinterpret_cast<const float4*>(sm + L::POSE + (3 + j0 + u) * S);
+    #pragma unroll
+                    for (int q = 0; q < S / 4; ++q) {
+                        const float4 v = br[q];
+                        a0[4 * q + 0] += cur[u].x * v.x; a0[4 * q + 1] += cur[u].x * v.y;
+                        a0[4 * q + 2] += cur[u].x * v.z; a0[4 * q + 3] += cur[u].x * v.w;
+                        a1[4 * q + 0] += cur[u].y * v.x; a1[4 * q + 1] += cur[u].y * v.y;
+                        a1[4 * q + 2] += cur[u].y * v.z; a1[4 * q + 3] += cur[u].y * v.w;
+                    }
+                }
+    #pragma unroll
+                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            }
+            const float pm0 = C.pmean[g * kPriorPad + 2 * ip], pm1 = C.pmean[g * kPriorPad + 2 * ip + 1];
+            float* o = sm + L::QT + (g * kPriorPad + 2 * ip) * S;
+    #pragma unroll
+            for (int s = 0; s < S; ++s) { o[s] = a0[s] - pm0; o[S + s] = a1[s] - pm1; }
+        }
     }
 }
 
