@@ -18,7 +18,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.environ.get('SMPLB200_LIB') or os.path.join(_HERE, 'libsmplify_b200.so')   # override: profiling builds only
-SOURCES = ['kernels.cu', 'lbs_tc.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
+SOURCES = ['kernels.cu', 'lbs_tc.cu', 'adjacent.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -157,6 +157,18 @@ def _declare(lib):
     lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
     lib.smplb200_probe_fp32_peak.restype = ci
     lib.smplb200_probe_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.smplb200_rot6d_to_rotmat.restype = ci
+    lib.smplb200_rot6d_to_rotmat.argtypes = [ci, vp, vp, vp]
+    lib.smplb200_rotmat_to_axis_angle.restype = ci
+    lib.smplb200_rotmat_to_axis_angle.argtypes = [ci, vp, vp, ci, vp]
+    lib.smplb200_estimate_translation.restype = ci
+    lib.smplb200_estimate_translation.argtypes = [ci, vp, vp, cf, cf, vp, vp]
+    lib.smplb200_fits_get.restype = ci
+    lib.smplb200_fits_get.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.smplb200_fits_set.restype = ci
+    lib.smplb200_fits_set.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.smplb200_keep_better.restype = ci
+    lib.smplb200_keep_better.argtypes = [ci] + [vp] * 12
     lib.smplb200_smplify_fit_host.restype = ci
     lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
     return lib
@@ -168,6 +180,8 @@ EXPORTED_SYMBOLS = (
     'smplb200_smplify_fitting_loss', 'smplb200_smpl_forward', 'smplb200_smpl_backward',
     'smplb200_batch_rodrigues', 'smplb200_batch_rodrigues_backward', 'smplb200_perspective_projection',
     'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count', 'smplb200_probe_fp32_peak',
+    'smplb200_rot6d_to_rotmat', 'smplb200_rotmat_to_axis_angle', 'smplb200_estimate_translation', 'smplb200_fits_get',
+    'smplb200_fits_set', 'smplb200_keep_better',
 )
 
 

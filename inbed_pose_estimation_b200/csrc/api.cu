@@ -333,6 +333,61 @@ extern "C" int smplb200_perspective_projection_backward(int batch, int num_point
     return 0;
 }
 
+// ---- the steps either side of SMPLify -------------------------------------------------------------------
+extern "C" int smplb200_rot6d_to_rotmat(int n, const float* x6, float* rotmat, void* stream) {
+    if (n < 0 || (n > 0 && (!x6 || !rotmat))) return fail("rot6d_to_rotmat: bad arguments");
+    CUDA_OK(launch_rot6d_to_rotmat(x6, rotmat, n, static_cast<cudaStream_t>(stream)));
+    if (n) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_rotmat_to_axis_angle(int n, const float* rotmat, float* axis_angle, int scrub_nan, void* stream) {
+    if (n < 0 || (n > 0 && (!rotmat || !axis_angle))) return fail("rotmat_to_axis_angle: bad arguments");
+    CUDA_OK(launch_rotmat_to_aa(rotmat, axis_angle, n, scrub_nan, static_cast<cudaStream_t>(stream)));
+    if (n) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_estimate_translation(int batch, const float* joints3d, const float* keypoints_2d, float focal_length,
+                                             float img_size, float* translation, void* stream) {
+    if (batch < 0 || (batch > 0 && (!joints3d || !keypoints_2d || !translation))) return fail("estimate_translation: bad arguments");
+    CUDA_OK(launch_estimate_translation(joints3d, keypoints_2d, focal_length, img_size, translation, batch, static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_fits_get(int batch, const float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
+                                 const int32_t* pose_flip_perm, float* pose, float* betas, void* stream) {
+    if (batch < 0 || (batch > 0 && (!store || !index || !rot_deg || !flipped || !pose_flip_perm || !pose || !betas)))
+        return fail("fits_get: bad arguments");
+    for (int i = 0; i < 72; ++i)
+        if (pose_flip_perm[i] < 0 || pose_flip_perm[i] >= 72) return fail("fits_get: pose_flip_perm[%d] out of range", i);
+    CUDA_OK(launch_fits_get(store, reinterpret_cast<const long long*>(index), rot_deg, flipped, pose_flip_perm, pose, betas, batch,
+                            static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_fits_set(int batch, float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
+                                 const uint8_t* update, const int32_t* pose_flip_perm, const float* pose, const float* betas,
+                                 void* stream) {
+    if (batch < 0 || (batch > 0 && (!store || !index || !rot_deg || !flipped || !update || !pose_flip_perm || !pose || !betas)))
+        return fail("fits_set: bad arguments");
+    for (int i = 0; i < 72; ++i)
+        if (pose_flip_perm[i] < 0 || pose_flip_perm[i] >= 72) return fail("fits_set: pose_flip_perm[%d] out of range", i);
+    CUDA_OK(launch_fits_set(store, reinterpret_cast<const long long*>(index), rot_deg, flipped, update, pose_flip_perm, pose, betas,
+                            batch, static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_keep_better(int batch, const float* new_reprojection_loss, const float* new_pose, const float* new_betas,
+                                    const float* new_cam_t, const float* new_joints, float* best_loss, float* best_pose,
+                                    float* best_betas, float* best_cam_t, float* best_joints, uint8_t* update, void* stream) {
+    if (batch < 0 || (batch > 0 && (!new_reprojection_loss || !new_pose || !new_betas || !new_cam_t || !best_loss || !best_pose ||
+                                    !best_betas || !best_cam_t || !update)))
+        return fail("keep_better: bad arguments");
+    CUDA_OK(launch_keep_better(new_reprojection_loss, new_pose, new_betas, new_cam_t, new_joints, best_loss, best_pose, best_betas,
+                               best_cam_t, best_joints, update, batch, static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+
 // Host-buffer wrapper: H2D of the five inputs, fit, D2H of the results, synchronise.
 extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, int num_iters, float step_size, float focal_length,
                                          const float* init_pose, const float* init_betas, const float* init_cam_t,

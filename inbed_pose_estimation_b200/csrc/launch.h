@@ -21,4 +21,17 @@ cudaError_t launch_projection_fwd(const float* pts, const float* rot, const floa
 cudaError_t launch_projection_bwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,
                                   const float* gout, float* gpts, float* grot, float* gtr, int batch, int npts, cudaStream_t st);
 
+// adjacent.cu: the steps either side of SMPLify in the reference's train step
+cudaError_t launch_rot6d_to_rotmat(const float* x, float* R, int n, cudaStream_t st);
+cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, int scrub_nan, cudaStream_t st);
+cudaError_t launch_estimate_translation(const float* S, const float* kp, float focal, float img_size, float* trans, int batch,
+                                        cudaStream_t st);
+cudaError_t launch_fits_get(const float* store, const long long* index, const float* rot, const uint8_t* flipped, const int* perm72,
+                            float* pose, float* betas, int batch, cudaStream_t st);
+cudaError_t launch_fits_set(float* store, const long long* index, const float* rot, const uint8_t* flipped, const uint8_t* update,
+                            const int* perm72, const float* pose, const float* betas, int batch, cudaStream_t st);
+cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, const float* new_betas, const float* new_cam,
+                               const float* new_joints, float* loss, float* pose, float* betas, float* cam, float* joints,
+                               uint8_t* update, int batch, cudaStream_t st);
+
 }  // namespace smplb200

@@ -93,3 +93,52 @@ def perspective_projection(points, rotation, translation, focal_length, camera_c
     else:
         focal = torch.full((1,), float(focal_length), device=points.device, dtype=torch.float32)
     return _Projection.apply(points, rotation, translation, focal, camera_center)
+
+
+# ---- the steps either side of SMPLify -----------------------------------------------------------------
+def rot6d_to_rotmat(x):
+    """6-D rotation representation -> rotation matrices (reference utils/geometry.py:47-61).
+    x: (B, 6) or anything viewable as (-1, 3, 2); returns (N, 3, 3).  Forward only: in the reference this op sits
+    inside the CNN regressors (out of scope); the SMPLify path consumes its detached output."""
+    _require_cuda(x, 'rot6d_to_rotmat')
+    x6 = x.detach().reshape(-1, 6).contiguous().float()
+    out = torch.empty((x6.shape[0], 3, 3), device=x6.device, dtype=torch.float32)
+    with torch.cuda.device(x6.device):
+        _native.check(_native.lib().smplb200_rot6d_to_rotmat(x6.shape[0], _native.ptr(x6), _native.ptr(out), _stream(x6.device)))
+    return out
+
+
+def rotmat_to_rot6d(matrix):
+    """Drop the last row (reference utils/geometry.py:64-77)."""
+    return matrix[..., :2, :].clone().reshape(*matrix.size()[:-2], 6)
+
+
+def rotation_matrix_to_angle_axis(rotation_matrix, scrub_nan=False):
+    """torchgeometry.rotation_matrix_to_angle_axis as the trainer uses it (train/trainer.py:702-706):
+    (N, 3, 3) or (N, 3, 4) rotation matrices -> (N, 3) axis-angle; scrub_nan=True also applies the trainer's
+    `pred_pose[torch.isnan(pred_pose)] = 0.0` patch in the same kernel."""
+    _require_cuda(rotation_matrix, 'rotation_matrix_to_angle_axis')
+    if rotation_matrix.dim() != 3 or rotation_matrix.shape[1] != 3 or rotation_matrix.shape[2] not in (3, 4):
+        raise ValueError('rotation_matrix must be (N, 3, 3) or (N, 3, 4)')
+    R = rotation_matrix.detach()[:, :, :3].contiguous().float()
+    out = torch.empty((R.shape[0], 3), device=R.device, dtype=torch.float32)
+    with torch.cuda.device(R.device):
+        _native.check(_native.lib().smplb200_rotmat_to_axis_angle(R.shape[0], _native.ptr(R), _native.ptr(out), int(bool(scrub_nan)),
+                                                                  _stream(R.device)))
+    return out
+
+
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=224.):
+    """Camera translation that best reprojects the 24 ground-truth joints (reference utils/geometry.py:156-181).
+    S: (B, 49, 3) 3-D joints, joints_2d: (B, 49, 3) (x, y, confidence) -> (B, 3).  The reference copies to the host
+    and solves one 3x3 system per sample with numpy; here one thread per sample does the same float64 arithmetic."""
+    _require_cuda(S, 'estimate_translation')
+    B = S.shape[0]
+    if tuple(S.shape) != (B, 49, 3) or tuple(joints_2d.shape) != (B, 49, 3):
+        raise ValueError('S and joints_2d must be (B, 49, 3)')
+    Sc, kp = S.detach().contiguous().float(), joints_2d.detach().to(S.device).contiguous().float()
+    out = torch.empty((B, 3), device=S.device, dtype=torch.float32)
+    with torch.cuda.device(S.device):
+        _native.check(_native.lib().smplb200_estimate_translation(B, _native.ptr(Sc), _native.ptr(kp), float(focal_length), float(img_size),
+                                                                  _native.ptr(out), _stream(S.device)))
+    return out

@@ -48,6 +48,32 @@ def keep_if_better(old_fits, old_loss, new_fits, new_loss):
     return fits, loss, update
 
 
+def keep_better_(best_loss, best_pose, best_betas, best_cam_t, new_reproj, new_pose, new_betas, new_cam_t,
+                 best_joints=None, new_joints=None):
+    """In-place CUDA form of the reference's bookkeeping after SMPLify (train/trainer.py:716-727), one kernel:
+    update = new_reproj.mean(-1) < best_loss; the best_* rows where it holds are overwritten.  Returns update (bool)."""
+    import ctypes
+    from . import _native
+    dev = best_loss.device
+    if dev.type != 'cuda':
+        raise RuntimeError('keep_better_ runs on CUDA tensors only (no CPU fallback)')
+    B = best_loss.shape[0]
+    for t in (best_loss, best_pose, best_betas, best_cam_t) + ((best_joints,) if best_joints is not None else ()):
+        if not (t.is_contiguous() and t.dtype == torch.float32 and t.device == dev):
+            raise ValueError('best_* tensors must be contiguous fp32 CUDA tensors (they are updated in place)')
+    c = lambda t: t.detach().to(dev).float().contiguous()
+    update = torch.zeros(B, dtype=torch.uint8, device=dev)
+    nj = c(new_joints) if (best_joints is not None and new_joints is not None) else None
+    if B:
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().smplb200_keep_better(
+                B, _native.ptr(c(new_reproj)), _native.ptr(c(new_pose)), _native.ptr(c(new_betas)), _native.ptr(c(new_cam_t)),
+                _native.ptr(nj), _native.ptr(best_loss), _native.ptr(best_pose), _native.ptr(best_betas), _native.ptr(best_cam_t),
+                _native.ptr(best_joints) if nj is not None else None, ctypes.c_void_p(update.data_ptr()),
+                torch.cuda.current_stream(dev).cuda_stream))
+    return update.bool()
+
+
 class ShardedRefit(object):
     """refit(fits [N,82], cam_t [N,3], center [N,2], keypoints [N,49,3], old_loss [N]) on every rank.
 

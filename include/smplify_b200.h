@@ -126,6 +126,35 @@ int smplb200_perspective_projection_backward(int batch, int num_points, const fl
                                              const float* grad_projected, float* grad_points, float* grad_rotation,
                                              float* grad_translation, void* stream);
 
+/* ---- the steps either side of SMPLify in the reference's train step ------------------------------- */
+
+/* utils/geometry.py:47-61 rot6d_to_rotmat: [n][6] (viewed [n][3][2]) -> [n][3][3]. */
+int smplb200_rot6d_to_rotmat(int n, const float* x6, float* rotmat, void* stream);
+
+/* train/trainer.py:702-706: torchgeometry.rotation_matrix_to_angle_axis on [n][3][3] rotation matrices
+ * (the homogeneous column the trainer appends is not read) and, with scrub_nan != 0, the NaN -> 0 patch. */
+int smplb200_rotmat_to_axis_angle(int n, const float* rotmat, float* axis_angle /*[n][3]*/, int scrub_nan, void* stream);
+
+/* utils/geometry.py:118-181 estimate_translation: per sample weighted least squares over the 24 ground-truth
+ * joint slots 25..48 of joints3d [B][49][3] and keypoints_2d [B][49][3] (x, y, conf), float64 inside. */
+int smplb200_estimate_translation(int batch, const float* joints3d, const float* keypoints_2d, float focal_length,
+                                  float img_size, float* translation /*[B][3]*/, void* stream);
+
+/* train/fits_dict.py:34-94 FitsDict.__getitem__ / __setitem__ on a device-resident store [N][82]
+ * (72 pose + 10 betas per image): gather + rotate + flip, and un-flip + un-rotate + masked scatter.
+ * index int64 [B], rot_deg fp32 [B], flipped / update uint8 [B], pose_flip_perm = the 72 entries of
+ * constants.SMPL_POSE_FLIP_PERM (host pointer).  Rows of one batch must have distinct indices. */
+int smplb200_fits_get(int batch, const float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
+                      const int32_t* pose_flip_perm, float* pose /*[B][72]*/, float* betas /*[B][10]*/, void* stream);
+int smplb200_fits_set(int batch, float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
+                      const uint8_t* update, const int32_t* pose_flip_perm, const float* pose, const float* betas, void* stream);
+
+/* train/trainer.py:716-727: update[b] = mean_j(new_reprojection_loss[b][j]) < best_loss[b]; where it holds the
+ * best_* rows are overwritten by the new fit (best_joints / new_joints [B][49][3] may both be NULL). */
+int smplb200_keep_better(int batch, const float* new_reprojection_loss /*[B][49]*/, const float* new_pose, const float* new_betas,
+                         const float* new_cam_t, const float* new_joints, float* best_loss /*[B]*/, float* best_pose,
+                         float* best_betas, float* best_cam_t, float* best_joints, uint8_t* update /*[B]*/, void* stream);
+
 /* Host-buffer convenience wrapper of smplb200_smplify_fit: all pointers are HOST pointers
  * (pinned for best throughput); copies inputs to the device, runs the fit, copies the results
  * back and synchronises.  vertices may be NULL (they are then left on the device and not

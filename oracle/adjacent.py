@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of the steps either side of SMPLify.
+
+Follows, in order: utils/geometry.py:47-61 (rot6d_to_rotmat), train/trainer.py:702-706 (rotmat -> axis-angle through
+torchgeometry + NaN scrub), utils/geometry.py:118-181 (estimate_translation), train/fits_dict.py:34-94 (FitsDict get /
+set with flip_pose :62-70 and rotate_pose :72-94, which calls cv2.Rodrigues per sample), train/trainer.py:716-727
+(keep-if-better).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.
+Pinned against tests/golden/adjacent.npz, which oracle/run_reference_adjacent.py produced by running the reference's
+own utils/geometry.py and train/fits_dict.py (torchgeometry through oracle/tgm_shim.py [recall], OpenCV real).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import tgm_shim
+
+POSE_FLIP_PERM = [3 * j + c for j in [0, 2, 1, 3, 5, 4, 6, 8, 7, 9, 11, 10, 12, 14, 13, 15, 17, 16, 19, 18, 21, 20, 23, 22]
+                  for c in range(3)]
+
+
+def rot6d_to_rotmat(x):
+    x = x.view(-1, 3, 2)
+    a1, a2 = x[:, :, 0], x[:, :, 1]
+    b1 = F.normalize(a1)
+    b2 = F.normalize(a2 - torch.einsum('bi,bi->b', b1, a2).unsqueeze(-1) * b1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    return torch.stack((b1, b2, b3), dim=-1)
+
+
+def rotmat_to_axis_angle(rotmat, scrub_nan=True):
+    """trainer.py:702-706 on [N,3,3] matrices."""
+    n = rotmat.shape[0]
+    hom = torch.cat([rotmat.view(-1, 3, 3), torch.tensor([0, 0, 1], dtype=torch.float32).view(1, 3, 1).expand(n, -1, -1)], dim=-1)
+    aa = tgm_shim.rotation_matrix_to_angle_axis(hom).contiguous()
+    if scrub_nan:
+        aa[torch.isnan(aa)] = 0.0
+    return aa
+
+
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=224.):
+    """float64 weighted least squares per sample over joints 25..48."""
+    S = S[:, 25:, :].double().numpy()
+    conf = joints_2d[:, 25:, 2].double().numpy()
+    uv = joints_2d[:, 25:, :2].double().numpy()
+    out = np.zeros((S.shape[0], 3), dtype=np.float32)
+    c = img_size / 2.
+    for i in range(S.shape[0]):
+        w = np.repeat(np.sqrt(conf[i]), 2)
+        Q = np.zeros((2 * S.shape[1], 3))
+        Q[0::2, 0] = focal_length
+        Q[1::2, 1] = focal_length
+        Q[:, 2] = c - uv[i].reshape(-1)
+        rhs = (uv[i].reshape(-1) - c) * np.repeat(S[i, :, 2], 2) - focal_length * S[i, :, :2].reshape(-1)
+        Q, rhs = Q * w[:, None], rhs * w
+        out[i] = np.linalg.solve(Q.T @ Q, Q.T @ rhs)
+    return torch.from_numpy(out)
+
+
+def flip_pose(pose, is_flipped):
+    is_flipped = is_flipped.bool()
+    out = pose.clone()
+    out[is_flipped, :] = pose[is_flipped][:, POSE_FLIP_PERM]
+    out[is_flipped, 1::3] *= -1
+    out[is_flipped, 2::3] *= -1
+    return out
+
+
+def rotate_pose(pose, rot):
+    import cv2
+    pose = pose.clone()
+    rot = rot.float()
+    cos, sin = torch.cos(-np.pi * rot / 180.), torch.sin(-np.pi * rot / 180.)
+    zeros = torch.zeros_like(cos)
+    r3 = torch.zeros(cos.shape[0], 1, 3)
+    r3[:, 0, -1] = 1
+    R = torch.cat([torch.stack([cos, -sin, zeros], dim=-1).unsqueeze(1), torch.stack([sin, cos, zeros], dim=-1).unsqueeze(1), r3], dim=1)
+    g = tgm_shim.angle_axis_to_rotation_matrix(pose[:, :3])[:, :3, :3]
+    g = torch.matmul(R, g).numpy()
+    aa = np.zeros((pose.shape[0], 3))
+    for i in range(pose.shape[0]):
+        v, _ = cv2.Rodrigues(g[i])
+        aa[i] = v.squeeze()
+    pose[:, :3] = torch.from_numpy(aa).to(pose.dtype)
+    return pose
+
+
+def fits_get(store, index, rot, is_flipped):
+    params = store[index]
+    return flip_pose(rotate_pose(params[:, :72].clone(), rot), is_flipped), params[:, 72:].clone()
+
+
+def fits_set(store, index, rot, is_flipped, update, pose, betas):
+    pose = rotate_pose(flip_pose(pose, is_flipped), -rot)
+    params = torch.cat((pose, betas), dim=-1)
+    for n, i in enumerate(index.tolist()):
+        if bool(update[n]):
+            store[i] = params[n]
+    return store
+
+
+def keep_better(best_loss, best_pose, best_betas, best_cam, new_reproj, new_pose, new_betas, new_cam):
+    new_loss = new_reproj.mean(dim=-1)
+    update = new_loss < best_loss
+    best_loss, best_pose, best_betas, best_cam = best_loss.clone(), best_pose.clone(), best_betas.clone(), best_cam.clone()
+    best_loss[update] = new_loss[update]
+    best_pose[update, :] = new_pose[update, :]
+    best_betas[update, :] = new_betas[update, :]
+    best_cam[update, :] = new_cam[update, :]
+    return best_loss, best_pose, best_betas, best_cam, update
