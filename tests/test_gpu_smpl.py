@@ -102,3 +102,23 @@ def test_zero_pose_and_errors(smpl):
     assert out0.vertices.shape == (0, 6890, 3) and out0.joints.shape == (0, 49, 3)
     with pytest.raises(RuntimeError, match='CUDA'):
         smpl(global_orient=torch.zeros(1, 3), body_pose=torch.zeros(1, 69), betas=torch.zeros(1, 10))
+
+
+def test_large_batch_rows_equal_small_batch_rows(smpl):
+    """Batch independence at a size that crosses the 16-sample pose tiles, several 128-sample MMA tiles and K splits:
+    the first rows of a 2100-sample call equal the same rows computed alone (forward bit for bit - a sample's MMA row
+    does not depend on its neighbours - gradients up to the different split-K partition)."""
+    inp = synthetic.make_fit_inputs(2100, seed=21)
+    gen = torch.Generator().manual_seed(3)
+    gv = torch.randn(2100, 6890, 3, generator=gen).cuda()
+    outs = []
+    for n in (2100, 37):
+        pose = torch.from_numpy(inp['pose'][:n]).cuda().requires_grad_(True)
+        betas = torch.from_numpy(inp['betas'][:n]).cuda().requires_grad_(True)
+        o = smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
+        (o.vertices * gv[:n]).sum().backward()
+        outs.append((o.vertices.detach()[:37].cpu(), o.joints.detach()[:37].cpu(), pose.grad[:37].cpu(), betas.grad[:37].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    np.testing.assert_allclose(outs[0][2].numpy(), outs[1][2].numpy(), rtol=2e-5, atol=2e-5 * float(outs[1][2].abs().max()))
+    np.testing.assert_allclose(outs[0][3].numpy(), outs[1][3].numpy(), rtol=2e-5, atol=2e-5 * float(outs[1][3].abs().max()))
+    assert torch.isfinite(outs[0][2]).all()
