@@ -18,7 +18,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIB_PATH = os.environ.get('SMPLB200_LIB') or os.path.join(_HERE, 'libsmplify_b200.so')   # override: profiling builds only
-SOURCES = ['kernels.cu', 'lbs_tc.cu', 'adjacent.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
+SOURCES = ['kernels.cu', 'lbs_tc.cu', 'adjacent.cu', 'train_losses.cu', 'api.cu', 'probe.cu', 'model_host.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
@@ -169,6 +169,18 @@ def _declare(lib):
     lib.smplb200_fits_set.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.smplb200_keep_better.restype = ci
     lib.smplb200_keep_better.argtypes = [ci] + [vp] * 12
+    lib.smplb200_finalize_fits.restype = ci
+    lib.smplb200_finalize_fits.argtypes = [ci, cf] + [vp] * 14
+    lib.smplb200_train_loss_workspace_bytes.restype = sz
+    lib.smplb200_train_loss_workspace_bytes.argtypes = [ci]
+    lib.smplb200_smpl_param_losses.restype = ci
+    lib.smplb200_smpl_param_losses.argtypes = [ci] + [vp] * 10
+    lib.smplb200_keypoint_loss.restype = ci
+    lib.smplb200_keypoint_loss.argtypes = [ci, vp, vp, cf, cf, vp, vp, vp, vp]
+    lib.smplb200_keypoint_3d_loss.restype = ci
+    lib.smplb200_keypoint_3d_loss.argtypes = [ci] + [vp] * 7
+    lib.smplb200_shape_loss.restype = ci
+    lib.smplb200_shape_loss.argtypes = [ci] + [vp] * 7
     lib.smplb200_smplify_fit_host.restype = ci
     lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
     return lib
@@ -181,7 +193,8 @@ EXPORTED_SYMBOLS = (
     'smplb200_batch_rodrigues', 'smplb200_batch_rodrigues_backward', 'smplb200_perspective_projection',
     'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count', 'smplb200_probe_fp32_peak',
     'smplb200_rot6d_to_rotmat', 'smplb200_rotmat_to_axis_angle', 'smplb200_estimate_translation', 'smplb200_fits_get',
-    'smplb200_fits_set', 'smplb200_keep_better',
+    'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
+    'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
 )
 
 

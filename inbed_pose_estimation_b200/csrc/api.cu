@@ -388,6 +388,58 @@ extern "C" int smplb200_keep_better(int batch, const float* new_reprojection_los
     return 0;
 }
 
+// ---- what the train step does with the SMPLify result ---------------------------------------------
+extern "C" int smplb200_finalize_fits(int batch, float smplify_threshold, const uint8_t* has_smpl, const float* gt_pose,
+                                      const float* gt_betas, const float* gt_cam_t, const float* gt_joints, const float* gt_vertices,
+                                      const float* opt_joint_loss, float* opt_pose, float* opt_betas, float* opt_cam_t,
+                                      float* opt_joints, float* opt_vertices, uint8_t* valid_fit, void* stream) {
+    if (batch < 0 || (batch > 0 && (!has_smpl || !gt_pose || !gt_betas || !gt_cam_t || !gt_joints || !opt_joint_loss || !opt_pose ||
+                                    !opt_betas || !opt_cam_t || !opt_joints || !valid_fit || (!opt_vertices != !gt_vertices))))
+        return fail("finalize_fits: bad arguments");
+    CUDA_OK(launch_finalize_fits(batch, smplify_threshold, has_smpl, gt_pose, gt_betas, gt_cam_t, gt_joints, gt_vertices, opt_joint_loss,
+                                 opt_pose, opt_betas, opt_cam_t, opt_joints, opt_vertices, valid_fit, static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+extern "C" size_t smplb200_train_loss_workspace_bytes(int batch) { return train_loss_workspace_doubles(batch) * sizeof(double); }
+extern "C" int smplb200_smpl_param_losses(int batch, const float* pred_rotmat, const float* pred_betas, const float* gt_pose,
+                                          const float* gt_betas, const uint8_t* valid, float* losses, float* grad_pred_rotmat,
+                                          float* grad_pred_betas, void* workspace, void* stream) {
+    if (batch < 0 || !losses || !workspace || (batch > 0 && (!pred_rotmat || !pred_betas || !gt_pose || !gt_betas || !valid)))
+        return fail("smpl_param_losses: bad arguments");
+    CUDA_OK(launch_smpl_param_losses(batch, pred_rotmat, pred_betas, gt_pose, gt_betas, valid, losses, grad_pred_rotmat, grad_pred_betas,
+                                     static_cast<double*>(workspace), static_cast<cudaStream_t>(stream)));
+    g_launches += batch ? 3 : 2;
+    return 0;
+}
+extern "C" int smplb200_keypoint_loss(int batch, const float* pred_keypoints_2d, const float* gt_keypoints_2d, float openpose_weight,
+                                      float gt_weight, float* loss, float* grad_pred, void* workspace, void* stream) {
+    if (batch < 0 || !loss || !workspace || (batch > 0 && (!pred_keypoints_2d || !gt_keypoints_2d)))
+        return fail("keypoint_loss: bad arguments");
+    CUDA_OK(launch_keypoint_loss(batch, pred_keypoints_2d, gt_keypoints_2d, openpose_weight, gt_weight, loss, grad_pred,
+                                 static_cast<double*>(workspace), static_cast<cudaStream_t>(stream)));
+    g_launches += batch ? 3 : 2;
+    return 0;
+}
+extern "C" int smplb200_keypoint_3d_loss(int batch, const float* pred_joints, const float* gt_keypoints_3d, const uint8_t* has_pose_3d,
+                                         float* loss, float* grad_pred_joints, void* workspace, void* stream) {
+    if (batch < 0 || !loss || !workspace || (batch > 0 && (!pred_joints || !gt_keypoints_3d || !has_pose_3d)))
+        return fail("keypoint_3d_loss: bad arguments");
+    CUDA_OK(launch_keypoint3d_loss(batch, pred_joints, gt_keypoints_3d, has_pose_3d, loss, grad_pred_joints,
+                                   static_cast<double*>(workspace), static_cast<cudaStream_t>(stream)));
+    g_launches += batch ? 3 : 2;
+    return 0;
+}
+extern "C" int smplb200_shape_loss(int batch, const float* pred_vertices, const float* gt_vertices, const uint8_t* valid, float* loss,
+                                   float* grad_pred_vertices, void* workspace, void* stream) {
+    if (batch < 0 || !loss || !workspace || (batch > 0 && (!pred_vertices || !gt_vertices || !valid)))
+        return fail("shape_loss: bad arguments");
+    CUDA_OK(launch_shape_loss(batch, pred_vertices, gt_vertices, valid, loss, grad_pred_vertices, static_cast<double*>(workspace),
+                              static_cast<cudaStream_t>(stream)));
+    g_launches += batch ? 3 : 2;
+    return 0;
+}
+
 // Host-buffer wrapper: H2D of the five inputs, fit, D2H of the results, synchronise.
 extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, int num_iters, float step_size, float focal_length,
                                          const float* init_pose, const float* init_betas, const float* init_cam_t,

@@ -34,4 +34,20 @@ cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, c
                                const float* new_joints, float* loss, float* pose, float* betas, float* cam, float* joints,
                                uint8_t* update, int batch, cudaStream_t st);
 
+
+// train_losses.cu: what the train step does with the SMPLify result
+size_t train_loss_workspace_doubles(int batch);
+cudaError_t launch_finalize_fits(int batch, float threshold, const uint8_t* has_smpl, const float* gt_pose, const float* gt_betas,
+                                 const float* gt_cam, const float* gt_joints, const float* gt_verts, const float* loss, float* pose,
+                                 float* betas, float* cam, float* joints, float* verts, uint8_t* valid_fit, cudaStream_t st);
+cudaError_t launch_smpl_param_losses(int batch, const float* pred_rotmat, const float* pred_betas, const float* gt_pose,
+                                     const float* gt_betas, const uint8_t* valid, float* losses2, float* grad_rotmat, float* grad_betas,
+                                     double* ws, cudaStream_t st);
+cudaError_t launch_keypoint_loss(int batch, const float* pred, const float* gt, float op_w, float gt_w, float* loss, float* grad_pred,
+                                 double* ws, cudaStream_t st);
+cudaError_t launch_keypoint3d_loss(int batch, const float* pred_joints, const float* gt, const uint8_t* has3d, float* loss,
+                                   float* grad_pred, double* ws, cudaStream_t st);
+cudaError_t launch_shape_loss(int batch, const float* pred, const float* gt, const uint8_t* valid, float* loss, float* grad_pred,
+                              double* ws, cudaStream_t st);
+
 }  // namespace smplb200

@@ -155,6 +155,41 @@ int smplb200_keep_better(int batch, const float* new_reprojection_loss /*[B][49]
                          const float* new_cam_t, const float* new_joints, float* best_loss /*[B]*/, float* best_pose,
                          float* best_betas, float* best_cam_t, float* best_joints, uint8_t* update /*[B]*/, void* stream);
 
+/* ---- what the train step does with the SMPLify result (train/trainer.py:735-772) ------------------- */
+
+/* train/trainer.py:735-748: opt_betas rows with any |beta| > 3 are zeroed; rows with has_smpl != 0 take the ground-truth
+ * pose / betas / cam_t / model joints [B][49][3] / vertices [B][6890][3] (opt_vertices and gt_vertices may both be NULL);
+ * valid_fit[b] = (opt_joint_loss[b] < smplify_threshold) | has_smpl[b].  All opt_* are updated in place. */
+int smplb200_finalize_fits(int batch, float smplify_threshold, const uint8_t* has_smpl, const float* gt_pose, const float* gt_betas,
+                           const float* gt_cam_t, const float* gt_joints, const float* gt_vertices, const float* opt_joint_loss,
+                           float* opt_pose, float* opt_betas, float* opt_cam_t, float* opt_joints, float* opt_vertices,
+                           uint8_t* valid_fit /*[B]*/, void* stream);
+
+/* Device scratch (bytes) of the four loss entry points below for a batch. */
+size_t smplb200_train_loss_workspace_bytes(int batch);
+
+/* Each loss call writes its scalar(s) to DEVICE memory and, when the grad pointer is not NULL, d(loss)/d(prediction)
+ * for an upstream gradient of 1 (rows outside the mask get zeros).  An empty mask gives loss 0 and zero gradients
+ * (the reference returns a zero tensor in that case).  No host synchronisation.
+ *
+ * train/trainer.py:165-178 smpl_losses: losses[0] = MSE(pred_rotmat[valid], batch_rodrigues(gt_pose)[valid]),
+ * losses[1] = MSE(pred_betas[valid], gt_betas[valid]); pred_rotmat [B][24][3][3], gt_pose [B][72]. */
+int smplb200_smpl_param_losses(int batch, const float* pred_rotmat, const float* pred_betas, const float* gt_pose,
+                               const float* gt_betas, const uint8_t* valid, float* losses /*[2]*/, float* grad_pred_rotmat,
+                               float* grad_pred_betas, void* workspace, void* stream);
+/* train/trainer.py:88-98 keypoint_loss: mean over [B][49][2] of conf * (pred - gt)^2, conf = gt[..,2] scaled by
+ * openpose_weight (slots 0..24) / gt_weight (slots 25..48). */
+int smplb200_keypoint_loss(int batch, const float* pred_keypoints_2d /*[B][49][2]*/, const float* gt_keypoints_2d /*[B][49][3]*/,
+                           float openpose_weight, float gt_weight, float* loss /*[1]*/, float* grad_pred, void* workspace,
+                           void* stream);
+/* train/trainer.py:100-117 keypoint_3d_loss: pred_joints [B][49][3] (slots 25..48 are read), gt_keypoints_3d [B][24][4]
+ * (x, y, z, conf), rows with has_pose_3d != 0, both pelvis-centred (mean of joints 2 and 3). */
+int smplb200_keypoint_3d_loss(int batch, const float* pred_joints, const float* gt_keypoints_3d, const uint8_t* has_pose_3d,
+                              float* loss /*[1]*/, float* grad_pred_joints /*[B][49][3]*/, void* workspace, void* stream);
+/* train/trainer.py:158-164 shape_loss: L1 mean over the [6890][3] vertices of the rows with valid != 0. */
+int smplb200_shape_loss(int batch, const float* pred_vertices, const float* gt_vertices, const uint8_t* valid, float* loss /*[1]*/,
+                        float* grad_pred_vertices, void* workspace, void* stream);
+
 /* Host-buffer convenience wrapper of smplb200_smplify_fit: all pointers are HOST pointers
  * (pinned for best throughput); copies inputs to the device, runs the fit, copies the results
  * back and synchronises.  vertices may be NULL (they are then left on the device and not

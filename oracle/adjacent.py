@@ -106,3 +106,89 @@ def keep_better(best_loss, best_pose, best_betas, best_cam, new_reproj, new_pose
     best_betas[update, :] = new_betas[update, :]
     best_cam[update, :] = new_cam[update, :]
     return best_loss, best_pose, best_betas, best_cam, update
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# What the train step does with the SMPLify result: restatement of train/trainer.py:88-117, 158-178
+# and 735-748, pinned by tests/golden/train_losses.npz (oracle/run_reference_trainer.py runs the reference's own source).
+# ---------------------------------------------------------------------------------------------------------------------
+def golden_vertex_pair(seed, n):
+    """The two [n,6890,3] vertex tensors of the train_losses golden cases (too large to commit; legacy RandomState
+    streams are frozen across numpy versions).  The first 100 vertices of row 0 coincide: exact zeros at the L1 kink."""
+    rs = np.random.RandomState(int(seed))
+    a = (rs.randn(n, 6890, 3) * 0.3).astype(np.float32)
+    b = (rs.randn(n, 6890, 3) * 0.3).astype(np.float32)
+    b[0, :100] = a[0, :100]
+    return a, b
+
+
+def keypoint_loss(pred_keypoints_2d, gt_keypoints_2d, openpose_weight, gt_weight):
+    """trainer.py:88-98."""
+    conf = gt_keypoints_2d[:, :, -1].unsqueeze(-1).clone()
+    conf[:, :25] *= openpose_weight
+    conf[:, 25:] *= gt_weight
+    return (conf * (pred_keypoints_2d - gt_keypoints_2d[:, :, :-1]) ** 2).mean()
+
+
+def keypoint_3d_loss(pred_keypoints_3d, gt_keypoints_3d, has_pose_3d):
+    """trainer.py:100-117 (0-dim zero instead of the reference's shape-[1] zero when no row has 3D labels)."""
+    sel = has_pose_3d != 0
+    pred = pred_keypoints_3d[:, 25:, :][sel]
+    conf = gt_keypoints_3d[:, :, -1].unsqueeze(-1)[sel]
+    gt = gt_keypoints_3d[:, :, :-1][sel]
+    if len(gt) == 0:
+        return pred_keypoints_3d.new_zeros(())
+    gt = gt - ((gt[:, 2, :] + gt[:, 3, :]) / 2)[:, None, :]
+    pred = pred - ((pred[:, 2, :] + pred[:, 3, :]) / 2)[:, None, :]
+    return (conf * (pred - gt) ** 2).mean()
+
+
+def shape_loss(pred_vertices, gt_vertices, has_smpl):
+    """trainer.py:158-164."""
+    sel = has_smpl != 0
+    if int(sel.sum()) == 0:
+        return pred_vertices.new_zeros(())
+    return (pred_vertices[sel] - gt_vertices[sel]).abs().mean()
+
+
+def quat_batch_rodrigues(theta):
+    """utils/geometry.py:9-45 (batch_rodrigues through quat_to_rotmat)."""
+    l1norm = torch.norm(theta + 1e-8, p=2, dim=1)
+    angle = l1norm.unsqueeze(-1)
+    normalized = theta / angle
+    angle = angle * 0.5
+    quat = torch.cat([torch.cos(angle), torch.sin(angle) * normalized], dim=1)
+    quat = quat / quat.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    w2, x2, y2, z2 = w * w, x * x, y * y, z * z
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1).view(-1, 3, 3)
+
+
+def smpl_losses(pred_rotmat, pred_betas, gt_pose, gt_betas, has_smpl):
+    """trainer.py:165-178."""
+    sel = has_smpl != 0
+    if int(sel.sum()) == 0:
+        z = pred_rotmat.new_zeros(())
+        return z, z.clone()
+    gt_rotmat = quat_batch_rodrigues(gt_pose.reshape(-1, 3)).view(-1, 24, 3, 3)
+    return ((pred_rotmat[sel] - gt_rotmat[sel]) ** 2).mean(), ((pred_betas[sel] - gt_betas[sel]) ** 2).mean()
+
+
+def finalize_fits(opt_pose, opt_betas, opt_cam_t, opt_joints, opt_vertices, opt_joint_loss, has_smpl,
+                  gt_pose, gt_betas, gt_cam_t, gt_model_joints, gt_vertices, smplify_threshold=100.):
+    """trainer.py:735-748 on copies; returns (pose, betas, cam_t, joints, vertices, valid_fit)."""
+    pose, betas, cam, joints = opt_pose.clone(), opt_betas.clone(), opt_cam_t.clone(), opt_joints.clone()
+    verts = opt_vertices.clone() if opt_vertices is not None else None
+    has = has_smpl != 0
+    betas[(betas.abs() > 3).any(dim=-1)] = 0.
+    if verts is not None:
+        verts[has] = gt_vertices[has]
+    cam[has] = gt_cam_t[has]
+    joints[has] = gt_model_joints[has]
+    pose[has] = gt_pose[has]
+    betas[has] = gt_betas[has]
+    valid_fit = (opt_joint_loss < smplify_threshold) | has
+    return pose, betas, cam, joints, verts, valid_fit
