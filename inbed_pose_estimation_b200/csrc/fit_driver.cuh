@@ -78,7 +78,7 @@ SB_HD SmallConsts stage_small_consts(const ModelView& M, float* sm) {
 template <int S>
 SB_HD void ph_chain_and_gemm_forward(const ModelView& M, float* sm) {
 #if defined(__CUDA_ARCH__)
-    if (S % 8 == 0 && TILE_NT == kFitTileThreads) {
+    if (kFastGemm<S> && TILE_NT == kFitTileThreads) {
         if (TILE_TID >= kChainWarpFirstThread) ph_chain_forward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
         else ph_fold_gemm_forward<S>(M, sm);
         TILE_SYNC();
@@ -95,7 +95,7 @@ SB_HD void ph_chain_and_gemm_forward(const ModelView& M, float* sm) {
 template <int S>
 SB_HD void ph_gemm_and_chain_backward(const ModelView& M, float* sm) {
 #if defined(__CUDA_ARCH__)
-    if (S % 8 == 0 && TILE_NT == kFitTileThreads) {
+    if (kFastGemm<S> && TILE_NT == kFitTileThreads) {
         if (TILE_TID >= kChainWarpFirstThread) ph_chain_backward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
         ph_fold_gemm_backward<S>(M, sm);              // warp 11 owns no GEMM range: it only joins the barriers and the combine
         TILE_SYNC();
@@ -122,11 +122,11 @@ SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, boo
 // Skinning transforms A = [G^R | A^t] and blend coefficients x of the tile's current pose, written as the hi/lo tf32
 // split operands of the tcgen05 vertex kernels (lbs_tc.cu): x [B][224], transforms [B][12 entries][24 joints + 8 pad].
 template <int S>
-SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, const TcOperands& tc) {
+SB_HD void tile_write_vertex_operands(float* sm, int first, int batch, const TcOperands& tc) {
     using L = TileLayout<S>;
     if (tc.x_hi) {
         FOR_ITEMS(it, S * kXPad) {
-            const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+            const int s = it / kXPad, k = it % kXPad, b = first + s;
             if (b >= batch) continue;
             const float x = sm[L::XT + k * S + s];
             const float hi = tf32_round(x);
@@ -136,7 +136,7 @@ SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, const TcOp
     }
     if (tc.ae_hi) {
         FOR_ITEMS(it, S * kAeRow) {
-            const int s = it / kAeRow, r = it % kAeRow, e = r / 32, j = r % 32, b = tile * S + s;
+            const int s = it / kAeRow, r = it % kAeRow, e = r / 32, j = r % 32, b = first + s;
             if (b >= batch) continue;
             float a = 0.f;
             if (j < kJoints) a = (e % 4 == 3) ? sm[L::AT + (3 * j + e / 4) * S + s] : sm[L::GW + (j * 12 + e) * S + s];
@@ -152,11 +152,11 @@ SB_HD void tile_write_vertex_operands(float* sm, int tile, int batch, const TcOp
 // 49 joints are an affine image of the root-identity pose:  joint = R0 (rest - sigma J0) + sigma J0.
 // One thread per sample runs the whole stage in registers.
 template <int S>
-SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int tile, float* sm) {
+SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     const AdamScalars* adam_tab = reinterpret_cast<const AdamScalars*>(sm + L::ADAMTAB);
     FOR_ITEMS(s, S) {
-        const int b = tile * S + s;
+        const int b = first + s;
         float th[3], t[3], mm[6], vv[6];
 #pragma unroll
         for (int a = 0; a < 3; ++a) { th[a] = sm[L::POSE + a * S + s]; t[a] = sm[L::CAM + a * S + s]; }
@@ -224,17 +224,17 @@ SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int tile, float
 }
 
 template <int S>
-SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int tile, float* sm) {
+SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     FOR_ITEMS(it, M.num_ign * S) {
-        const int s = it % S, o = M.ign_joints[it / S], b = tile * S + s;
+        const int s = it % S, o = M.ign_joints[it / S], b = first + s;
         sm[L::KP + (3 * o + 2) * S + s] = 0.f;
         if (b < P.batch) P.keypoints[((size_t)b * kOut + o) * 3 + 2] = 0.f;   // in place, smplify.py:105 / :156
     }
 }
 
 template <int S>
-SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm) {
+SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     // per-iteration Adam scalars, computed in float64 like torch does on the host
     AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::ADAMTAB);
@@ -247,34 +247,34 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
     }
     // ---- load the tile ---------------------------------------------------------------------
     FOR_ITEMS(it, S * 72) {
-        const int s = it / 72, k = it % 72, b = tile * S + s;
+        const int s = it / 72, k = it % 72, b = first + s;
         sm[L::POSE + k * S + s] = (b < P.batch) ? P.init_pose[(size_t)b * 72 + k] : 0.f;
     }
     FOR_ITEMS(it, S * kBetas) {
-        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        const int s = it / kBetas, k = it % kBetas, b = first + s;
         sm[L::BETA + k * S + s] = (b < P.batch) ? P.init_betas[(size_t)b * kBetas + k] : 0.f;
     }
     FOR_ITEMS(it, S * 3) {
-        const int s = it / 3, k = it % 3, b = tile * S + s;
+        const int s = it / 3, k = it % 3, b = first + s;
         sm[L::CAM + k * S + s] = (b < P.batch) ? P.init_cam[(size_t)b * 3 + k] : (k == 2 ? 1.f : 0.f);
     }
     FOR_ITEMS(it, S * 2) {
-        const int s = it / 2, k = it % 2, b = tile * S + s;
+        const int s = it / 2, k = it % 2, b = first + s;
         sm[L::CEN + k * S + s] = (b < P.batch) ? P.center[(size_t)b * 2 + k] : 0.f;
     }
     FOR_ITEMS(it, S * 147) {
-        const int s = it / 147, k = it % 147, b = tile * S + s;
+        const int s = it / 147, k = it % 147, b = first + s;
         sm[L::KP + k * S + s] = (b < P.batch) ? P.keypoints[(size_t)b * 147 + k] : 0.f;
     }
     TILE_SYNC();
-    if (P.zero_conf_first) { tile_zero_ignored_conf<S>(M, P, tile, sm); TILE_SYNC(); }
+    if (P.zero_conf_first) { tile_zero_ignored_conf<S>(M, P, first, sm); TILE_SYNC(); }
 
     if (P.num_iters > 0) {
         // ---- stage 1: global orientation + camera translation --------------------------------
         tile_forward<S>(M, C, sm, true, /*root_identity=*/true);
-        stage1_camera<S>(M, P, tile, sm);
+        stage1_camera<S>(M, P, first, sm);
         TILE_SYNC();
-        tile_zero_ignored_conf<S>(M, P, tile, sm);
+        tile_zero_ignored_conf<S>(M, P, first, sm);
         zero_rows<S>(sm, L::ADM, 2 * kParams);
         TILE_SYNC();
 
@@ -302,7 +302,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
             TILE_SYNC();
             if (P.loss_trace) {
                 FOR_ITEMS(s, S) {
-                    const int b = tile * S + s;
+                    const int b = first + s;
                     float a = 0.f;
                     for (int o = 0; o < kOut; ++o) a += sm[L::LOSSJ + o * S + s];
                     a = ((a + sm[L::LOSSJ + 49 * S + s]) + sm[L::LOSSJ + 50 * S + s]) + sm[L::LOSSJ + 51 * S + s];
@@ -349,27 +349,27 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int tile, float* sm)
     // ---- final forward: joints, per-joint reprojection loss, A and x for the vertex kernel --------
     tile_forward<S>(M, C, sm, true, false);
     FOR_ITEMS(it, S * 147) {
-        const int s = it / 147, k = it % 147, b = tile * S + s;
+        const int s = it / 147, k = it % 147, b = first + s;
         if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, tile, P.batch, P.tc);
+    tile_write_vertex_operands<S>(sm, first, P.batch, P.tc);
     TILE_SYNC();
     ph_reprojection<S>(sm, P.focal, kSigma2, false);
     TILE_SYNC();
     FOR_ITEMS(it, S * kOut) {
-        const int s = it / kOut, o = it % kOut, b = tile * S + s;
+        const int s = it / kOut, o = it % kOut, b = first + s;
         if (b < P.batch) P.out_reproj[(size_t)b * kOut + o] = sm[L::LOSSJ + o * S + s];
     }
     FOR_ITEMS(it, S * 72) {
-        const int s = it / 72, k = it % 72, b = tile * S + s;
+        const int s = it / 72, k = it % 72, b = first + s;
         if (P.out_pose && b < P.batch) P.out_pose[(size_t)b * 72 + k] = sm[L::POSE + k * S + s];
     }
     FOR_ITEMS(it, S * kBetas) {
-        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        const int s = it / kBetas, k = it % kBetas, b = first + s;
         if (P.out_betas && b < P.batch) P.out_betas[(size_t)b * kBetas + k] = sm[L::BETA + k * S + s];
     }
     FOR_ITEMS(it, S * 3) {
-        const int s = it / 3, k = it % 3, b = tile * S + s;
+        const int s = it / 3, k = it % 3, b = first + s;
         if (P.out_cam && b < P.batch) P.out_cam[(size_t)b * 3 + k] = sm[L::CAM + k * S + s];
     }
 }
@@ -394,51 +394,51 @@ struct PoseParams {
 };
 
 template <int S>
-SB_HD void pose_load(const PoseParams& P, int tile, float* sm) {
+SB_HD void pose_load(const PoseParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     if (P.rotmat_mode) {
         FOR_ITEMS(it, S * 216) {
-            const int s = it / 216, k = it % 216, b = tile * S + s;
+            const int s = it / 216, k = it % 216, b = first + s;
             sm[L::RM + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 216 + k] : ((k % 9) % 4 == 0 ? 1.f : 0.f);
         }
     } else {
         FOR_ITEMS(it, S * 72) {
-            const int s = it / 72, k = it % 72, b = tile * S + s;
+            const int s = it / 72, k = it % 72, b = first + s;
             sm[L::POSE + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 72 + k] : 0.f;
         }
     }
     FOR_ITEMS(it, S * kBetas) {
-        const int s = it / kBetas, k = it % kBetas, b = tile * S + s;
+        const int s = it / kBetas, k = it % kBetas, b = first + s;
         sm[L::BETA + k * S + s] = (b < P.batch) ? P.betas[(size_t)b * kBetas + k] : 0.f;
     }
     TILE_SYNC();
 }
 
 template <int S>
-SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
+SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     const SmallConsts C = stage_small_consts<S>(M, sm);
-    pose_load<S>(P, tile, sm);
+    pose_load<S>(P, first, sm);
     tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
-        const int s = it / 147, k = it % 147, b = tile * S + s;
+        const int s = it / 147, k = it % 147, b = first + s;
         if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, tile, P.batch, P.tc);
+    tile_write_vertex_operands<S>(sm, first, P.batch, P.tc);
 }
 
 template <int S>
-SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile, float* sm) {
+SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first, float* sm) {
     using L = TileLayout<S>;
     const SmallConsts C = stage_small_consts<S>(M, sm);
-    pose_load<S>(P, tile, sm);
+    pose_load<S>(P, first, sm);
     tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
-        const int s = it / 147, k = it % 147, b = tile * S + s;
+        const int s = it / 147, k = it % 147, b = first + s;
         sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
     }
     FOR_ITEMS(it, S * 288) {
-        const int s = it / 288, k = it % 288, b = tile * S + s;
+        const int s = it / 288, k = it % 288, b = first + s;
         float a = 0.f;
         if (P.dA_part && b < P.batch) {
             const int j = k / 12, e = k % 12;
@@ -454,7 +454,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
     ph_gemm_and_chain_backward<S>(M, sm);
     if (P.dx_part) {
         FOR_ITEMS(it, S * kXPad) {
-            const int s = it / kXPad, k = it % kXPad, b = tile * S + s;
+            const int s = it / kXPad, k = it % kXPad, b = first + s;
             if (b < P.batch) {
                 float a = sm[L::XT + k * S + s];
                 for (int sp = 0; sp < P.nsplit_x; ++sp) a += P.dx_part[((size_t)sp * P.batch + b) * kXPad + k];
@@ -464,7 +464,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
         TILE_SYNC();
     }
     FOR_ITEMS(it, kJoints * S) {
-        const int s = it % S, j = it / S, b = tile * S + s;
+        const int s = it % S, j = it / S, b = first + s;
         float g[9];
         rotation_grad<S>(sm, j, s, g);
         if (b >= P.batch) continue;
@@ -480,7 +480,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int tile,
         }
     }
     FOR_ITEMS(it, kBetas * S) {
-        const int s = it % S, l = it / S, b = tile * S + s;
+        const int s = it % S, l = it / S, b = first + s;
         const float g = beta_grad<S>(C, sm, l, s);
         if (b < P.batch) P.d_betas[(size_t)b * kBetas + l] = g;
     }

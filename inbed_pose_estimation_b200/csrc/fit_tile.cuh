@@ -276,105 +276,152 @@ SB_HD float4 ld_const4(const float4* p) {
 #endif
 }
 
-// 4-column x 8-sample register tile, acc[c][s] += w[c] * v[s].  On the device the samples are packed in
-// pairs and updated with Blackwell's packed fp32 FMA (fma.rn.f32x2 via __ffma2_rn): scalar FFMA issues at
-// half rate on sm_100, the 2-wide form is what reaches the fp32 peak.  Results are bit-identical to scalar fmaf.
-struct Tile4x8 {
+// 4-column x (2 NP)-sample register tile, acc[c][s] += w[c] * v[s]  (NP = 4: 8 samples, NP = 3: 6 samples).  On the
+// device the samples are packed in pairs and updated with Blackwell's packed fp32 FMA (fma.rn.f32x2 via __ffma2_rn):
+// scalar FFMA issues at half rate on sm_100, the 2-wide form is what reaches the fp32 peak.  Results are bit-identical
+// to scalar fmaf.
+template <int NP>
+struct TileAcc {
+    static constexpr int NS = 2 * NP;
 #if defined(__CUDA_ARCH__)
-    float2 a[4][4];
+    float2 a[4][NP];
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int p = 0; p < 4; ++p) a[c][p] = make_float2(0.f, 0.f);
+            for (int p = 0; p < NP; ++p) a[c][p] = make_float2(0.f, 0.f);
     }
-    __device__ __forceinline__ void fma(const float4& w, const float4& v0, const float4& v1) {
-        const float2 vp[4] = {make_float2(v0.x, v0.y), make_float2(v0.z, v0.w), make_float2(v1.x, v1.y), make_float2(v1.z, v1.w)};
+    __device__ __forceinline__ void fma(const float4& w, const float2 (&vp)[NP]) {
         const float2 wp[4] = {make_float2(w.x, w.x), make_float2(w.y, w.y), make_float2(w.z, w.z), make_float2(w.w, w.w)};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int p = 0; p < 4; ++p) a[c][p] = __ffma2_rn(wp[c], vp[p], a[c][p]);
+            for (int p = 0; p < NP; ++p) a[c][p] = __ffma2_rn(wp[c], vp[p], a[c][p]);
     }
-    __device__ __forceinline__ float4 lo(int c) const { return make_float4(a[c][0].x, a[c][0].y, a[c][1].x, a[c][1].y); }
-    __device__ __forceinline__ float4 hi(int c) const { return make_float4(a[c][2].x, a[c][2].y, a[c][3].x, a[c][3].y); }
+    __device__ __forceinline__ float get(int c, int s) const { return (s & 1) ? a[c][s >> 1].y : a[c][s >> 1].x; }
 #else
-    float a[4][8];
+    float a[4][NS];
     void clear() {
         for (int c = 0; c < 4; ++c)
-            for (int s = 0; s < 8; ++s) a[c][s] = 0.f;
+            for (int s = 0; s < NS; ++s) a[c][s] = 0.f;
     }
-    void fma(const float4& w, const float4& v0, const float4& v1) {
+    void fma(const float4& w, const float2 (&vp)[NP]) {
         const float ww[4] = {w.x, w.y, w.z, w.w};
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         for (int c = 0; c < 4; ++c)
-            for (int s = 0; s < 8; ++s) a[c][s] = fmaf(ww[c], vv[s], a[c][s]);
+            for (int p = 0; p < NP; ++p) {
+                a[c][2 * p] = fmaf(ww[c], vp[p].x, a[c][2 * p]);
+                a[c][2 * p + 1] = fmaf(ww[c], vp[p].y, a[c][2 * p + 1]);
+            }
     }
-    float4 lo(int c) const { return make_float4(a[c][0], a[c][1], a[c][2], a[c][3]); }
-    float4 hi(int c) const { return make_float4(a[c][4], a[c][5], a[c][6], a[c][7]); }
+    float get(int c, int s) const { return a[c][s]; }
 #endif
+    // column c of the tile -> dst[0 .. NS): 16-byte stores where the tile is 8 samples wide, 8-byte ones otherwise
+    SB_HD void store(float* dst, int c, float sub = 0.f) const {
+        if constexpr (NP == 4) {
+            float4* o = reinterpret_cast<float4*>(dst);
+            o[0] = make_float4(get(c, 0) - sub, get(c, 1) - sub, get(c, 2) - sub, get(c, 3) - sub);
+            o[1] = make_float4(get(c, 4) - sub, get(c, 5) - sub, get(c, 6) - sub, get(c, 7) - sub);
+        } else {
+            float2* o = reinterpret_cast<float2*>(dst);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) o[p] = make_float2(get(c, 2 * p) - sub, get(c, 2 * p + 1) - sub);
+        }
+    }
 };
 
-// acc[c][s] += sum_{k < K} w[k * ldw4][c] * x[k * ldx + s]  for the 4 columns of one float4 column quad and 8 samples:
+// Tile shapes of the GEMM fast paths: 8 samples per thread where S is a multiple of 8, 6 where S = 12 (the tile size that
+// fills the second wave of batches such as 4096 = 148 x 16 + 144 x 12).
+template <int S> constexpr bool kFastGemm = (S % 8 == 0) || (S == 12);
+template <int S> constexpr int kTileSamples = (S % 8 == 0) ? 8 : 6;
+
+// One row of x for a tile: NP sample pairs starting at x (16-byte aligned when NP = 4, 8-byte aligned otherwise).
+template <int NP>
+SB_HD void load_x_row(const float* x, float2 (&v)[NP]) {
+    if constexpr (NP == 4) {
+        const float4 v0 = reinterpret_cast<const float4*>(x)[0], v1 = reinterpret_cast<const float4*>(x)[1];
+        v[0] = make_float2(v0.x, v0.y); v[1] = make_float2(v0.z, v0.w); v[2] = make_float2(v1.x, v1.y); v[3] = make_float2(v1.z, v1.w);
+    } else {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) v[p] = reinterpret_cast<const float2*>(x)[p];
+    }
+}
+
+// acc[c][s] += sum_{k < K} w[k * ldw4][c] * x[k * ldx + s]  for the 4 columns of one float4 column quad and 2 NP samples:
 // the streamed-constant GEMM core of the three GEMM phases.  The constant rows come from L2 in groups of 4, two groups
-// ahead, through three register sets used in rotation (no register moves in the steady state); the x row of the next
-// k-step is fetched from shared memory while the current one is multiplied.  Measured in isolation on B200
-// (tools/exp/gemm_probe.cu): 70 % of the fp32 FMA peak against 57 % for the plain two-deep prefetch loop.
-template <int K>
-SB_HD void stream_gemm_4x8(Tile4x8& acc, const float4* w, int ldw4, const float* x, int ldx) {
+// ahead, through three register sets used in rotation; the x row of the next k-step is fetched from shared memory while
+// the current one is multiplied.  Measured in isolation on B200 (tools/exp/gemm_probe.cu): 70 % of the fp32 FMA peak
+// against 57 % for the plain two-deep prefetch loop.
+template <int K, int LDW4, int LDX, int NP>
+SB_HD void stream_gemm(TileAcc<NP>& acc, const float4* w, const float* x) {
     constexpr int U = 4, G = K / U;
     static_assert(K % U == 0 && G >= 2, "K must be a multiple of 4, at least 8");
     float4 ca[U], cb[U], cc[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { ca[u] = ld_const4(w + u * ldw4); cb[u] = ld_const4(w + (U + u) * ldw4); cc[u] = cb[u]; }
-    float4 v0 = reinterpret_cast<const float4*>(x)[0], v1 = reinterpret_cast<const float4*>(x)[1];
-    auto step = [&](const float4 (&cur)[U], float4 (&nxt)[U], int g) {
-        if (g + 2 < G) {
+    for (int u = 0; u < U; ++u) { ca[u] = ld_const4(w + u * LDW4); cb[u] = ld_const4(w + (U + u) * LDW4); cc[u] = cb[u]; }
+    float2 v[NP];
+    load_x_row<NP>(x, v);
+    // one group of U rows at (wg, xg), held in cur: fetch the group two ahead into nxt, multiply, keep x one row ahead.
+    // All offsets from wg / xg are compile-time constants (immediate-offset loads, no per-load address arithmetic).
+    auto step = [&](const float4 (&cur)[U], float4 (&nxt)[U], const float4* wg, const float* xg, bool prefetch, bool last) {
+        if (prefetch) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) nxt[u] = ld_const4(w + ((g + 2) * U + u) * ldw4);
+            for (int u = 0; u < U; ++u) nxt[u] = ld_const4(wg + (2 * U + u) * LDW4);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int kn = (g * U + u + 1 < K) ? g * U + u + 1 : g * U + u;      // next row (the last one is re-read, unused)
-            const float4* xr = reinterpret_cast<const float4*>(x + kn * ldx);
-            const float4 n0 = xr[0], n1 = xr[1];
-            acc.fma(cur[u], v0, v1);
-            v0 = n0; v1 = n1;
+            const int kn = (last && u == U - 1) ? u : u + 1;                     // next row (the very last one is re-read, unused)
+            float2 n[NP];
+            load_x_row<NP>(xg + kn * LDX, n);
+            acc.fma(cur[u], v);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) v[p] = n[p];
         }
     };
     constexpr int ROUNDS = (G - 2) / 3, TAIL = G - 3 * ROUNDS;          // TAIL in {2, 3, 4}
-#pragma unroll 1
+    constexpr int UNR = (ROUNDS % 3 == 0) ? 3 : ((ROUNDS <= 6) ? ROUNDS : ((ROUNDS % 2 == 0) ? 2 : 1));
+    const float4* wg = w;
+    const float* xg = x;
+#pragma unroll UNR
     for (int r = 0; r < ROUNDS; ++r) {
-        step(ca, cc, 3 * r);
-        step(cb, ca, 3 * r + 1);
-        step(cc, cb, 3 * r + 2);
+        step(ca, cc, wg, xg, true, false);
+        step(cb, ca, wg + U * LDW4, xg + U * LDX, true, false);
+        step(cc, cb, wg + 2 * U * LDW4, xg + 2 * U * LDX, true, false);
+        wg += 3 * U * LDW4;
+        xg += 3 * U * LDX;
     }
-    step(ca, cc, 3 * ROUNDS);
-    step(cb, ca, 3 * ROUNDS + 1);
-    if (TAIL > 2) step(cc, cb, 3 * ROUNDS + 2);
-    if (TAIL > 3) step(ca, cc, 3 * ROUNDS + 3);
+    step(ca, cc, wg, xg, TAIL > 2, false);
+    step(cb, ca, wg + U * LDW4, xg + U * LDX, TAIL > 3, TAIL == 2);
+    if (TAIL > 2) step(cc, cb, wg + 2 * U * LDW4, xg + 2 * U * LDX, false, TAIL == 3);
+    if (TAIL > 3) step(ca, cc, wg + 3 * U * LDW4, xg + 3 * U * LDX, false, true);
+}
+
+// Work item -> (column item p, sample group h) of a GEMM phase with H sample groups.  With two groups the two threads that
+// share a column item sit in the same warp (lanes l and l + 16): their constant loads coalesce into one request, so every
+// constant is fetched once per CTA instead of once per sample group (the streamed constants are the L2-bandwidth term).
+template <int H>
+SB_HD void gemm_item(int t, int& p, int& h) {
+    static_assert(H == 1 || H == 2, "one or two sample groups");
+    if (H == 2) { p = (t >> 5) * 16 + (t & 15); h = (t >> 4) & 1; }
+    else { p = t; h = 0; }
 }
 
 // QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
 // S % 8 == 0: one thread owns 4 adjacent columns x 8 samples (32 accumulators, 1 LDG.128 + 2 LDS.128 per
 // 32 FMAs); the basis rows are streamed from L2 two groups of U rows ahead, x is broadcast from smem.
 template <int S>
-SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
+SB_HD_CALL void ph_fold_gemm_forward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
-    if constexpr (S % 8 == 0) {
-        constexpr int NQ4 = kQPad / 4, H = S / 8;       // 176 column quads, H sample groups
+    if constexpr (kFastGemm<S>) {
+        constexpr int TS = kTileSamples<S>, NQ4 = kQPad / 4, H = S / TS;       // 176 column quads, H sample groups
         FOR_ITEMS(t, NQ4 * H) {
-            const int cq = t % NQ4, h = t / NQ4;
-            Tile4x8 acc;
+            int cq, h;
+            gemm_item<H>(t, cq, h);
+            TileAcc<TS / 2> acc;
             acc.clear();
-            stream_gemm_4x8<kXPad>(acc, reinterpret_cast<const float4*>(M.Cf) + cq, NQ4, sm + L::XT + 8 * h, S);
+            stream_gemm<kXPad, NQ4, S>(acc, reinterpret_cast<const float4*>(M.Cf) + cq, sm + L::XT + TS * h);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float4* qo = reinterpret_cast<float4*>(sm + L::QT + (4 * cq + c) * L::LDQ + 8 * h);
-                qo[0] = acc.lo(c);
-                qo[1] = acc.hi(c);
-            }
+            for (int c = 0; c < 4; ++c) acc.store(sm + L::QT + (4 * cq + c) * L::LDQ + TS * h, c);
         }
     } else {
         FOR_ITEMS(n, kQPad) {
@@ -393,36 +440,33 @@ SB_HD void ph_fold_gemm_forward(const ModelView& M, float* sm) {
 }
 
 // dx[m][s] = sum_n Cf[m][n] * dQ[n][s]   (transpose GEMM; result overwrites XT).
-// Device fast path (S % 8 == 0, >= 384 threads): thread = (n-range r of 3, sample group h, column quad mq of
+// Device fast path (S a multiple of 8 or S = 12, >= 384 threads): thread = (n-range r of 3, sample group h, column quad mq of
 // 56), 4 x 8 accumulators; the three partial sums are combined in a fixed order through the (by then dead)
 // QT region - deterministic, no atomics.
 template <int S>
-SB_HD void ph_fold_gemm_backward(const ModelView& M, float* sm) {
+SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
 #if defined(__CUDA_ARCH__)
-    if constexpr (S % 8 == 0) {
-        constexpr int MQ = kXPad / 4, H = S / 8, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
+    if constexpr (kFastGemm<S>) {
+        constexpr int TS = kTileSamples<S>, MQ = kXPad / 4, H = S / TS, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
         static_assert(NR * NPER <= kQPad && NR * NPER >= kQ && NPER % 4 == 0, "n ranges");
-        constexpr int PER_R = MQ * H;                                          // 112 threads per range when S = 16
-        if (TILE_NT >= PER_R * NR) {
-            const int tid = TILE_TID, r = tid / PER_R, w = tid % PER_R, mq = w % MQ, h = w / MQ;
-            const bool active = r < NR;
-            Tile4x8 acc;
+        if (TILE_NT >= MQ * NR * H) {
+            int p, h;
+            gemm_item<H>(TILE_TID, p, h);
+            const int r = p / MQ, mq = p % MQ;
+            const bool active = p < MQ * NR;                 // the chain warp (threads >= 352) maps to p >= 176: never active
+            TileAcc<TS / 2> acc;
             acc.clear();
             if (active) {
                 const int n_begin = r * NPER;
-                stream_gemm_4x8<NPER>(acc, reinterpret_cast<const float4*>(M.CfT) + (size_t)n_begin * MQ + mq, MQ,
-                                      sm + L::QT + n_begin * L::LDQ + 8 * h, L::LDQ);
+                stream_gemm<NPER, MQ, L::LDQ>(acc, reinterpret_cast<const float4*>(M.CfT) + (size_t)n_begin * MQ + mq,
+                                              sm + L::QT + n_begin * L::LDQ + TS * h);
             }
             TILE_SYNC();                               // everyone is done reading dQ: QT becomes scratch
             if (active) {
                 float* dst = (r == 0) ? (sm + L::XT) : (sm + L::QT + (r - 1) * kXPad * S);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float4* d = reinterpret_cast<float4*>(dst + (4 * mq + c) * S + 8 * h);
-                    d[0] = acc.lo(c);
-                    d[1] = acc.hi(c);
-                }
+                for (int c = 0; c < 4; ++c) acc.store(dst + (4 * mq + c) * S + TS * h, c);
             }
             TILE_SYNC();
             FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = (sm[L::XT + i] + sm[L::QT + i]) + sm[L::QT + kXPad * S + i];
@@ -533,28 +577,23 @@ SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad)
 // Pd[(g,i)][s] = sum_j Psym_g[i][j] * bp[j][s] - (Psym_g mean_g)[i]   for all 8 components: an
 // [S x 72] . [72 x 576] GEMM streamed like the folded one (two adjacent i per thread).
 template <int S>
-SB_HD void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
+SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
-    if constexpr (S % 8 == 0) {
-        // 4 adjacent i x 8 samples per thread through the streamed-constant GEMM core (rows j >= 69 of Psym are zero;
-        // the pose rows they meet - the first betas - are finite)
-        constexpr int IQ = kPriorPad / 4, H = S / 8;        // 18 column quads per component
+    if constexpr (kFastGemm<S>) {
+        // 4 adjacent i x 8 (or 6) samples per thread through the streamed-constant GEMM core (rows j >= 69 of Psym are
+        // zero; the pose rows they meet - the first betas - are finite)
+        constexpr int TS = kTileSamples<S>, IQ = kPriorPad / 4, H = S / TS;        // 18 column quads per component
         FOR_ITEMS(t, kGauss * IQ * H) {
-            const int h = t / (kGauss * IQ), gi = t % (kGauss * IQ), g = gi / IQ, iq = gi % IQ;
-            Tile4x8 acc;
+            int gi, h;
+            gemm_item<H>(t, gi, h);
+            const int g = gi / IQ, iq = gi % IQ;
+            TileAcc<TS / 2> acc;
             acc.clear();
-            stream_gemm_4x8<kPriorPad>(acc, reinterpret_cast<const float4*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + iq, IQ,
-                                       sm + L::POSE + 3 * S + 8 * h, S);
+            stream_gemm<kPriorPad, IQ, S>(acc, reinterpret_cast<const float4*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + iq,
+                                          sm + L::POSE + 3 * S + TS * h);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float pm = C.pmean[g * kPriorPad + 4 * iq + c];
-                float4 lo = acc.lo(c), hi = acc.hi(c);
-                lo.x -= pm; lo.y -= pm; lo.z -= pm; lo.w -= pm;
-                hi.x -= pm; hi.y -= pm; hi.z -= pm; hi.w -= pm;
-                float4* o = reinterpret_cast<float4*>(sm + L::QT + (g * kPriorPad + 4 * iq + c) * S + 8 * h);
-                o[0] = lo;
-                o[1] = hi;
-            }
+            for (int c = 0; c < 4; ++c)
+                acc.store(sm + L::QT + (g * kPriorPad + 4 * iq + c) * S + TS * h, c, C.pmean[g * kPriorPad + 4 * iq + c]);
         }
     } else {
         constexpr int U = 8, IP = kPriorPad / 2;        // 36 column pairs per component

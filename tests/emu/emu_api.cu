@@ -79,7 +79,7 @@ extern "C" int emu_fit(EmuModel* m, int batch, int num_iters, float step_size, f
     P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
     P.adam_c.lerp_w = (float)(1.0 - 0.9); P.adam_c.beta2 = (float)0.999; P.adam_c.w2 = (float)(1.0 - 0.999); P.adam_c.eps = 1e-8f;
     std::vector<float> sm = tile_scratch();
-    for (int t = 0; t < (batch + S - 1) / S; ++t) fit_tile<S>(m->H.view, P, t, sm.data());
+    for (int t = 0; t < (batch + S - 1) / S; ++t) fit_tile<S>(m->H.view, P, t * S, sm.data());
     ops.unpack(batch, ws_A, ws_x);
     return 0;
 }
@@ -104,8 +104,8 @@ extern "C" int emu_pose(EmuModel* m, int batch, int rotmat_mode, int backward, c
     P.d_pose = d_pose; P.d_betas = d_betas;
     std::vector<float> sm = tile_scratch();
     for (int t = 0; t < (batch + S - 1) / S; ++t) {
-        if (backward) pose_backward_tile<S>(m->H.view, P, t, sm.data());
-        else pose_forward_tile<S>(m->H.view, P, t, sm.data());
+        if (backward) pose_backward_tile<S>(m->H.view, P, t * S, sm.data());
+        else pose_forward_tile<S>(m->H.view, P, t * S, sm.data());
     }
     if (!backward) ops.unpack(batch, ws_A, ws_x);
     return 0;
