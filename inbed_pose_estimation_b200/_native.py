@@ -35,32 +35,63 @@ def _nvcc():
     return None
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def _source_hash():
+    """Digest of everything the library is built from (file names + contents): staleness must not depend on file times,
+    which a copy of the tree (the GPU box's snapshot) does not preserve."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
     deps.append(os.path.join(os.path.dirname(_HERE), 'include', 'smplify_b200.h'))
-    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+    for d in deps:
+        if os.path.isfile(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, 'rb') as f:
+                h.update(f.read())
+    h.update(' '.join(NVCC_FLAGS + SOURCES).encode())
+    return h.hexdigest()
+
+
+def _stale(lib_path=None):
+    lib_path = lib_path or LIB_PATH
+    if not os.path.exists(lib_path):
+        return True
+    try:
+        with open(lib_path + '.srchash') as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False, extra_flags=(), out=None):
-    """Compile the CUDA library for sm_100a into the package directory."""
+    """Compile the CUDA library for sm_100a into the package directory.  Safe to call from several processes at once
+    (one rank per GPU): an exclusive file lock serialises the builders and the later ones find the library fresh."""
+    import fcntl
     out = out or LIB_PATH
     if out == LIB_PATH and not force and not _stale():
         return LIB_PATH
-    nvcc = _nvcc()
-    if nvcc is None:
-        raise RuntimeError('nvcc not found: cannot build %s' % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', out + '.tmp'] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + res.stdout)
-    os.replace(out + '.tmp', out)
-    if verbose:
-        print(res.stdout)
-    return out
+    with open(out + '.lock', 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if out == LIB_PATH and not force and not _stale():
+                return LIB_PATH                                  # another process built it while we waited
+            nvcc = _nvcc()
+            if nvcc is None:
+                raise RuntimeError('nvcc not found: cannot build %s' % out)
+            tmp = '%s.tmp.%d' % (out, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + \
+                ['-o', tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+            if res.returncode != 0:
+                raise RuntimeError('nvcc failed:\n' + res.stdout)
+            os.replace(tmp, out)
+            if not extra_flags:
+                with open(out + '.srchash', 'w') as f:
+                    f.write(_source_hash())
+            if verbose:
+                print(res.stdout)
+            return out
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 _f32p = ctypes.POINTER(ctypes.c_float)

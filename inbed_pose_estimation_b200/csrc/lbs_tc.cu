@@ -362,15 +362,17 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
                 }
             }
         };
-        float iv[8][3], nx[8][3];
+        // two chunks ahead: the kernel is bound by latency x bytes in flight (8 consumer warps per SM), not by issue slots
+        float iv[8][3], nx[8][3], nx2[8][3];
         fetch(g, nx);
+        fetch(g + groups, nx2);
         for (int c = g; c < nchunks; c += groups) {
             const int b0 = c * SK_NB + half * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int a = 0; a < 3; ++a) iv[i][a] = nx[i][a];
-            fetch(c + groups, nx);
+                for (int a = 0; a < 3; ++a) { iv[i][a] = nx[i][a]; nx[i][a] = nx2[i][a]; }
+            fetch(c + 2 * groups, nx2);
             mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
             tc_fence_after();
             const uint32_t ta = tmem_base + lane_bits + t.stage * SK_N + half * 96;
