@@ -234,7 +234,7 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            if _stale():
+            if not os.environ.get('SMPLB200_LIB') and _stale():      # an explicitly named library is loaded as it is
                 build()
             _lib = _declare(ctypes.CDLL(LIB_PATH))
         return _lib

@@ -490,59 +490,103 @@ SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     }
 }
 
-// One of the 54 source joints of sample s (chain joint, skinned picked vertex, folded extra joint).
-template <int S>
-SB_HD void source_joint(const SmallConsts& C, const float* sm, int src, int s, float* P) {
-    using L = TileLayout<S>;
-    if (src < kJoints) {
-        P[0] = sm[L::GW + (src * 12 + 3) * S + s];
-        P[1] = sm[L::GW + (src * 12 + 7) * S + s];
-        P[2] = sm[L::GW + (src * 12 + 11) * S + s];
-    } else if (src < kJoints + kSelVerts) {
-        const int p = src - kJoints;                    // only p < kPicks is ever requested
-        float T[12];
-#pragma unroll
-        for (int e = 0; e < 12; ++e) T[e] = 0.f;
-        for (int j = 0; j < kJoints; ++j) {
-            const float w = C.Wp[p * kJoints + j];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) T[r * 4 + c] += w * sm[L::GW + (j * 12 + r * 4 + c) * S + s];
-                T[r * 4 + 3] += w * sm[L::AT + (3 * j + r) * S + s];
-            }
-        }
-        const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
-                    vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) P[r] = T[r * 4 + 0] * vx + T[r * 4 + 1] * vy + T[r * 4 + 2] * vz + T[r * 4 + 3];
-    } else {
-        const int k = src - (kJoints + kSelVerts);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int j = 0; j < kJoints; ++j) {
-            const int qb = (k * kJoints + j) * 3;
-            const float qx = sm[L::QT + (qb + 0) * L::LDQ + s], qy = sm[L::QT + (qb + 1) * L::LDQ + s], qz = sm[L::QT + (qb + 2) * L::LDQ + s];
-            const float w = C.wkj[k * kJoints + j];
-            const float* G = sm + L::GW + (j * 12) * S + s;
-            a0 += G[0 * S] * qx + G[1 * S] * qy + G[2 * S] * qz + sm[L::AT + (3 * j + 0) * S + s] * w;
-            a1 += G[4 * S] * qx + G[5 * S] * qy + G[6 * S] * qz + sm[L::AT + (3 * j + 1) * S + s] * w;
-            a2 += G[8 * S] * qx + G[9 * S] * qy + G[10 * S] * qz + sm[L::AT + (3 * j + 2) * S + s] * w;
-        }
-        P[0] = a0; P[1] = a1; P[2] = a2;
-    }
-}
-
-// The 49 output joints into OUTJ.
+// The 20 "heavy" source joints - the 9 folded extra joints E_k = sum_j G_j^R Q_kj + A_j^t w_kj and the 11 skinned picked
+// vertices P_p = sum_j Wp[p][j] (G_j^R v_p + A_j^t) - are sums over the 24 joints that all read the same G_j^R, A_j^t.
+// A work item is (sample, quarter of the joints, block of <= 5 extras or <= 3 picks): the 12 shared transform entries of
+// a joint are loaded once per item instead of once per (source, joint), and every source is computed once even when two
+// outputs map to it.  The four partial positions per source go to a scratch area (the DG rows, dead until the
+// reprojection phase clears them) and are added in a fixed order when the outputs are gathered.
+constexpr int kHeavy = kExtra + kPicks;                 // 20 sources: picks 0..10, extras 11..19
+constexpr int kJointParts = 4;                         // the 24 joints in 4 runs of 6
 template <int S>
 SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
+    constexpr int JN = kJoints / kJointParts, EB = 5, PB = 3;
+    constexpr int NEB = (kExtra + EB - 1) / EB, NPB = (kPicks + PB - 1) / PB;      // 2 extra blocks, 4 pick blocks
+    static_assert(kHeavy * 3 * kJointParts <= 288, "partial positions must fit in the DG rows");
+    float* scr = sm + L::DG;                              // [(heavy source * 3 + coordinate) * kJointParts + third][S]
+    constexpr int PER_BLK = (kJointParts * S + 31) / 32 * 32;      // whole warps per block: extras and picks never share a warp
+    FOR_ITEMS(it, (NEB + NPB) * PER_BLK) {
+        const int blk = it / PER_BLK, idx = it % PER_BLK, s = idx % S, t = idx / S;
+        if (t >= kJointParts) continue;
+        if (blk < NEB) {
+            const int k0 = blk * EB;
+            float acc[EB][3];
+#pragma unroll
+            for (int i = 0; i < EB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+            for (int j = t * JN; j < (t + 1) * JN; ++j) {
+                const float* G = sm + L::GW + (j * 12) * S + s;
+                const float g0 = G[0 * S], g1 = G[1 * S], g2 = G[2 * S], g4 = G[4 * S], g5 = G[5 * S], g6 = G[6 * S],
+                            g8 = G[8 * S], g9 = G[9 * S], g10 = G[10 * S];
+                const float t0 = sm[L::AT + (3 * j + 0) * S + s], t1 = sm[L::AT + (3 * j + 1) * S + s], t2 = sm[L::AT + (3 * j + 2) * S + s];
+#pragma unroll
+                for (int i = 0; i < EB; ++i) {
+                    const int k = k0 + i;
+                    if (k < kExtra) {
+                        const int qb = (k * kJoints + j) * 3;
+                        const float qx = sm[L::QT + (qb + 0) * L::LDQ + s], qy = sm[L::QT + (qb + 1) * L::LDQ + s],
+                                    qz = sm[L::QT + (qb + 2) * L::LDQ + s];
+                        const float w = C.wkj[k * kJoints + j];
+                        acc[i][0] += g0 * qx + g1 * qy + g2 * qz + t0 * w;
+                        acc[i][1] += g4 * qx + g5 * qy + g6 * qz + t1 * w;
+                        acc[i][2] += g8 * qx + g9 * qy + g10 * qz + t2 * w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < EB; ++i)
+                if (k0 + i < kExtra) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) scr[(((kPicks + k0 + i) * 3 + c) * kJointParts + t) * S + s] = acc[i][c];
+                }
+        } else {
+            const int p0 = (blk - NEB) * PB;
+            float acc[PB][3], v[PB][3];
+#pragma unroll
+            for (int i = 0; i < PB; ++i) {
+                acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
+                const int p = (p0 + i < kPicks) ? p0 + i : kPicks - 1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[i][c] = sm[L::QT + (kQPickBase + 3 * p + c) * L::LDQ + s];
+            }
+            for (int j = t * JN; j < (t + 1) * JN; ++j) {
+                const float* G = sm + L::GW + (j * 12) * S + s;
+                const float g0 = G[0 * S], g1 = G[1 * S], g2 = G[2 * S], g4 = G[4 * S], g5 = G[5 * S], g6 = G[6 * S],
+                            g8 = G[8 * S], g9 = G[9 * S], g10 = G[10 * S];
+                const float t0 = sm[L::AT + (3 * j + 0) * S + s], t1 = sm[L::AT + (3 * j + 1) * S + s], t2 = sm[L::AT + (3 * j + 2) * S + s];
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    const int p = (p0 + i < kPicks) ? p0 + i : kPicks - 1;
+                    const float w = C.Wp[p * kJoints + j];
+                    acc[i][0] += w * (g0 * v[i][0] + g1 * v[i][1] + g2 * v[i][2] + t0);
+                    acc[i][1] += w * (g4 * v[i][0] + g5 * v[i][1] + g6 * v[i][2] + t1);
+                    acc[i][2] += w * (g8 * v[i][0] + g9 * v[i][1] + g10 * v[i][2] + t2);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PB; ++i)
+                if (p0 + i < kPicks) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) scr[(((p0 + i) * 3 + c) * kJointParts + t) * S + s] = acc[i][c];
+                }
+        }
+    }
+    TILE_SYNC();
+    // gather the 49 outputs: a chain joint is the translation of its world transform, a heavy source the sum of its partials
     FOR_ITEMS(it, kOut * S) {
-        const int s = it % S, o = it / S;
-        float P[3];
-        source_joint<S>(C, sm, M.joint_map[o], s, P);
-        sm[L::OUTJ + (3 * o + 0) * S + s] = P[0];
-        sm[L::OUTJ + (3 * o + 1) * S + s] = P[1];
-        sm[L::OUTJ + (3 * o + 2) * S + s] = P[2];
+        const int s = it % S, o = it / S, src = M.joint_map[o];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v;
+            if (src < kJoints) {
+                v = sm[L::GW + (src * 12 + 4 * c + 3) * S + s];
+            } else {
+                const int h = (src < kJoints + kSelVerts) ? src - kJoints : kPicks + (src - (kJoints + kSelVerts));   // picks < kPicks only
+                const float* q = scr + ((h * 3 + c) * kJointParts) * S + s;
+                v = ((q[0] + q[S]) + q[2 * S]) + q[3 * S];
+            }
+            sm[L::OUTJ + (3 * o + c) * S + s] = v;
+        }
     }
 }
 
@@ -700,11 +744,30 @@ SB_HD void source_grad(const ModelView& M, const float* sm, int src, int s, floa
     }
 }
 
-// dL/dA_j from the extra joints and the picked vertices, converted to dL/dG_j and dL/dJ_j.
-// extern_dA (may be null): additional dL/dA [24][12] rows per sample coming from the vertex path.
+// Gradients arriving at the 20 heavy source joints (kHeavy: picks 0..10, extras 11..19), gathered once per sample into the
+// XT rows - x is dead between the forward and the backward folded GEMM - instead of once per (joint, source).
+template <int S>
+SB_HD void ph_source_grads(const ModelView& M, float* sm) {
+    using L = TileLayout<S>;
+    static_assert(kHeavy * 3 <= kXPad, "source gradients must fit in the XT rows");
+    FOR_ITEMS(it, kHeavy * S) {
+        const int s = it % S, h = it / S;
+        const int src = (h < kPicks) ? kJoints + h : kJoints + kSelVerts + (h - kPicks);
+        float d[3];
+        source_grad<S>(M, sm, src, s, d);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm[L::XT + (3 * h + c) * S + s] = d[c];
+    }
+}
+
+// dL/dA_j from the extra joints and the picked vertices, converted to dL/dG_j and dL/dJ_j.  DG holds additional dL/dA
+// rows on entry (zero in the fit, the vertex path's dA in SMPL backward).  Starts with ph_source_grads + a tile barrier.
 template <int S>
 SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
+    ph_source_grads<S>(M, sm);
+    TILE_SYNC();
+    const float* SG = sm + L::XT;
     FOR_ITEMS(it, kJoints * S) {
         const int s = it % S, j = it / S;
         float dAR[9], dAt[3];
@@ -718,8 +781,7 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
 #pragma unroll
             for (int c = 0; c < 3; ++c) G[r * 3 + c] = sm[L::GW + (j * 12 + r * 4 + c) * S + s];
         for (int k = 0; k < kExtra; ++k) {
-            float dE[3];
-            source_grad<S>(M, sm, kJoints + kSelVerts + k, s, dE);
+            const float dE[3] = {SG[(3 * (kPicks + k) + 0) * S + s], SG[(3 * (kPicks + k) + 1) * S + s], SG[(3 * (kPicks + k) + 2) * S + s]};
             const int qb = (k * kJoints + j) * 3;
             float* q0 = sm + L::QT + (qb + 0) * L::LDQ + s;
             float* q1 = sm + L::QT + (qb + 1) * L::LDQ + s;
@@ -736,8 +798,7 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
             *q2 = G[2] * dE[0] + G[5] * dE[1] + G[8] * dE[2];
         }
         for (int p = 0; p < kPicks; ++p) {
-            float dV[3];
-            source_grad<S>(M, sm, kJoints + p, s, dV);
+            const float dV[3] = {SG[(3 * p + 0) * S + s], SG[(3 * p + 1) * S + s], SG[(3 * p + 2) * S + s]};
             const float w = C.Wp[p * kJoints + j];
             const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
                         vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
@@ -765,14 +826,15 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
     }
 }
 
-// dL/d(v_posed of picked vertex) = (sum_j Wp[p][j] G_j^R)^T dL/dvert ; written over the pick rows of QT.
+// dL/d(v_posed of picked vertex) = (sum_j Wp[p][j] G_j^R)^T dL/dvert ; written over the pick rows of QT.  Reads the source
+// gradients ph_joint_backward left in XT; runs after it (a tile barrier in between: it overwrites the pick rows that phase reads).
 template <int S>
 SB_HD void ph_pick_backward(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
+    const float* SG = sm + L::XT;
     FOR_ITEMS(it, kPicks * S) {
         const int s = it % S, p = it / S;
-        float dV[3];
-        source_grad<S>(M, sm, kJoints + p, s, dV);
+        const float dV[3] = {SG[(3 * p + 0) * S + s], SG[(3 * p + 1) * S + s], SG[(3 * p + 2) * S + s]};
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
