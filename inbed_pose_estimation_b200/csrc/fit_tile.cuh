@@ -315,6 +315,17 @@ struct TileAcc {
     }
     float get(int c, int s) const { return a[c][s]; }
 #endif
+    // dst[0 .. NS) += column c of the tile (dst 8-byte aligned): second half of a split reduction
+    SB_HD void add_into(float* dst, int c) const {
+        float2* o = reinterpret_cast<float2*>(dst);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float2 v = o[p];
+            v.x += get(c, 2 * p);
+            v.y += get(c, 2 * p + 1);
+            o[p] = v;
+        }
+    }
     // column c of the tile -> dst[0 .. NS): 16-byte stores where the tile is 8 samples wide, 8-byte ones otherwise
     SB_HD void store(float* dst, int c, float sub = 0.f) const {
         if constexpr (NP == 4) {
@@ -331,8 +342,12 @@ struct TileAcc {
 
 // Tile shapes of the GEMM fast paths: 8 samples per thread where S is a multiple of 8, 6 where S = 12 (the tile size that
 // fills the second wave of batches such as 4096 = 148 x 16 + 144 x 12).
-template <int S> constexpr bool kFastGemm = (S % 8 == 0) || (S == 12);
-template <int S> constexpr int kTileSamples = (S % 8 == 0) ? 8 : 6;
+template <int S> constexpr bool kFastGemm = (S % 8 == 0) || (S == 12) || (S == 4);
+template <int S> constexpr int kTileSamples = (S % 8 == 0) ? 8 : ((S == 12) ? 6 : 4);
+// Tiles with one sample group (S = 4, 8) leave half of the 384 threads without a GEMM item, and a warp alone on its
+// scheduler cannot hide the latency of the streamed constants: the device splits the reduction (K) dimension of the three
+// GEMMs over the idle threads instead and adds the partial sums in a fixed order.
+template <int S> constexpr bool kSplitK = kFastGemm<S> && (S / kTileSamples<S> == 1);
 
 // One row of x for a tile: NP sample pairs starting at x (16-byte aligned when NP = 4, 8-byte aligned otherwise).
 template <int NP>
@@ -340,6 +355,9 @@ SB_HD void load_x_row(const float* x, float2 (&v)[NP]) {
     if constexpr (NP == 4) {
         const float4 v0 = reinterpret_cast<const float4*>(x)[0], v1 = reinterpret_cast<const float4*>(x)[1];
         v[0] = make_float2(v0.x, v0.y); v[1] = make_float2(v0.z, v0.w); v[2] = make_float2(v1.x, v1.y); v[3] = make_float2(v1.z, v1.w);
+    } else if constexpr (NP == 2) {
+        const float4 v0 = reinterpret_cast<const float4*>(x)[0];
+        v[0] = make_float2(v0.x, v0.y); v[1] = make_float2(v0.z, v0.w);
     } else {
 #pragma unroll
         for (int p = 0; p < NP; ++p) v[p] = reinterpret_cast<const float2*>(x)[p];
@@ -412,6 +430,29 @@ template <int S>
 SB_HD_CALL void ph_fold_gemm_forward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
+#if defined(__CUDA_ARCH__)
+    if constexpr (kSplitK<S>) {
+        // called by the 352 GEMM threads of the standard tile (the chain warp is busy elsewhere): thread = (column quad, K half)
+        constexpr int NQ4 = kQPad / 4, KH = kXPad / 2;
+        if (TILE_NT == kFitTileThreads) {
+            const int t = TILE_TID, cq = t % NQ4, ks = t / NQ4;
+            TileAcc<S / 2> acc;
+            acc.clear();
+            if (t < 2 * NQ4)
+                stream_gemm<KH, NQ4, S>(acc, reinterpret_cast<const float4*>(M.Cf) + cq + (size_t)ks * KH * NQ4, sm + L::XT + ks * KH * S);
+            if (t < NQ4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc.store(sm + L::QT + (4 * cq + c) * L::LDQ, c);
+            }
+            if (t < 2 * NQ4) asm volatile("bar.sync 1, %0;" ::"n"(2 * NQ4) : "memory");       // the GEMM threads only
+            if (t >= NQ4 && t < 2 * NQ4) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc.add_into(sm + L::QT + (4 * cq + c) * L::LDQ, c);
+            }
+            return;
+        }
+    }
+#endif
     if constexpr (kFastGemm<S>) {
         constexpr int TS = kTileSamples<S>, NQ4 = kQPad / 4, H = S / TS;       // 176 column quads, H sample groups
         FOR_ITEMS(t, NQ4 * H) {
@@ -448,8 +489,12 @@ SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
     using L = TileLayout<S>;
 #if defined(__CUDA_ARCH__)
     if constexpr (kFastGemm<S>) {
-        constexpr int TS = kTileSamples<S>, MQ = kXPad / 4, H = S / TS, NR = 3, NPER = 232;    // 3 x 232 = 696 <= 704 padded rows
+        // n ranges: 3 x 232 rows with two sample groups; with one group the idle threads take more, shorter ranges
+        // (S = 8: 4 x 176, S = 4: 6 x 116; rows >= 681 of CfT are zero padding)
+        constexpr int TS = kTileSamples<S>, MQ = kXPad / 4, H = S / TS;
+        constexpr int NR = (H == 2) ? 3 : ((S == 8) ? 4 : 6), NPER = (H == 2) ? 232 : ((S == 8) ? 176 : 116);
         static_assert(NR * NPER <= kQPad && NR * NPER >= kQ && NPER % 4 == 0, "n ranges");
+        static_assert((NR - 1) * kXPad * S <= kQPad * L::LDQ, "partial sums must fit in the QT region");
         if (TILE_NT >= MQ * NR * H) {
             int p, h;
             gemm_item<H>(TILE_TID, p, h);
@@ -469,7 +514,12 @@ SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
                 for (int c = 0; c < 4; ++c) acc.store(dst + (4 * mq + c) * S + TS * h, c);
             }
             TILE_SYNC();
-            FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = (sm[L::XT + i] + sm[L::QT + i]) + sm[L::QT + kXPad * S + i];
+            FOR_ITEMS(i, kXPad * S) {
+                float a = sm[L::XT + i];
+#pragma unroll
+                for (int r2 = 1; r2 < NR; ++r2) a += sm[L::QT + (r2 - 1) * kXPad * S + i];
+                sm[L::XT + i] = a;
+            }
             return;
         }
     }
@@ -623,6 +673,29 @@ SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad)
 template <int S>
 SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
     using L = TileLayout<S>;
+#if defined(__CUDA_ARCH__)
+    if constexpr (kSplitK<S>) {
+        constexpr int IQ = kPriorPad / 4, KH = kPriorPad / 2, NI = kGauss * IQ;        // 144 (component, column quad) items x 2 K halves
+        if (TILE_NT >= 2 * NI) {
+            const int t = TILE_TID, gi = t % NI, ks = t / NI, g = gi / IQ, iq = gi % IQ;
+            TileAcc<S / 2> acc;
+            acc.clear();
+            if (t < 2 * NI)
+                stream_gemm<KH, IQ, S>(acc, reinterpret_cast<const float4*>(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad) + iq + (size_t)ks * KH * IQ,
+                                       sm + L::POSE + (3 + ks * KH) * S);
+            if (t < NI) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc.store(sm + L::QT + (g * kPriorPad + 4 * iq + c) * S, c, C.pmean[g * kPriorPad + 4 * iq + c]);
+            }
+            TILE_SYNC();
+            if (t >= NI && t < 2 * NI) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc.add_into(sm + L::QT + (g * kPriorPad + 4 * iq + c) * S, c);
+            }
+            return;
+        }
+    }
+#endif
     if constexpr (kFastGemm<S>) {
         // 4 adjacent i x 8 (or 6) samples per thread through the streamed-constant GEMM core (rows j >= 69 of Psym are
         // zero; the pose rows they meet - the first betas - are finite)

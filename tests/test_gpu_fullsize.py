@@ -52,7 +52,10 @@ def test_lbs_65536_rows_and_linearity():
         assert torch.isfinite(big.vertices).all() and torch.isfinite(big.joints).all()
         for lo, hi in ((0, 19), (N - 33, N), (31000, 31017)):
             small = smpl(global_orient=pose[lo:hi, :3], body_pose=pose[lo:hi, 3:], betas=betas[lo:hi])
-            assert torch.equal(big.vertices[lo:hi], small.vertices) and torch.equal(big.joints[lo:hi], small.joints)
+            # vertices: the tensor-core path gives a sample's row the same bits in any batch; joints: the folded GEMM of
+            # small tiles splits its reduction differently (fp32 rounding only)
+            assert torch.equal(big.vertices[lo:hi], small.vertices)
+            np.testing.assert_allclose(big.joints[lo:hi].cpu().numpy(), small.joints.cpu().numpy(), rtol=0, atol=2e-6)
         del big
     # backward at full size: d/dpose of <g, vertices> is linear in g  (g1, g2 drawn once; grad(g1 + 2 g2) = grad(g1) + 2 grad(g2))
     gen = torch.Generator(device='cuda').manual_seed(5)

@@ -106,8 +106,8 @@ def test_zero_pose_and_errors(smpl):
 
 def test_large_batch_rows_equal_small_batch_rows(smpl):
     """Batch independence at a size that crosses the 16-sample pose tiles, several 128-sample MMA tiles and K splits:
-    the first rows of a 2100-sample call equal the same rows computed alone (forward bit for bit - a sample's MMA row
-    does not depend on its neighbours - gradients up to the different split-K partition)."""
+    the first rows of a 2100-sample call equal the same rows computed alone (vertices bit for bit - a sample's MMA row
+    does not depend on its neighbours - joints and gradients up to the different split-K partitions)."""
     inp = synthetic.make_fit_inputs(2100, seed=21)
     gen = torch.Generator().manual_seed(3)
     gv = torch.randn(2100, 6890, 3, generator=gen).cuda()
@@ -118,7 +118,8 @@ def test_large_batch_rows_equal_small_batch_rows(smpl):
         o = smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
         (o.vertices * gv[:n]).sum().backward()
         outs.append((o.vertices.detach()[:37].cpu(), o.joints.detach()[:37].cpu(), pose.grad[:37].cpu(), betas.grad[:37].cpu()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])
+    np.testing.assert_allclose(outs[0][1].numpy(), outs[1][1].numpy(), rtol=0, atol=2e-6)    # joints: small tiles split the folded GEMM's reduction
     np.testing.assert_allclose(outs[0][2].numpy(), outs[1][2].numpy(), rtol=2e-5, atol=2e-5 * float(outs[1][2].abs().max()))
     np.testing.assert_allclose(outs[0][3].numpy(), outs[1][3].numpy(), rtol=2e-5, atol=2e-5 * float(outs[1][3].abs().max()))
     assert torch.isfinite(outs[0][2]).all()
