@@ -243,13 +243,13 @@ def run_ours(a):
                'sample': '%d fits (100+100 iterations), 1 warm-up + 1 timed call, oracle/port.py eager torch fp32' % a.ref_batch}
 
     if rank == 0:
-        # which fit kernel ran (mirrors plan_fit_tiles in csrc/kernels.cu: whole waves of 16-sample tiles, then 12-sample tiles)
+        # which fit kernel ran
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        rest = B - (B // (16 * sms)) * 16 * sms
-        if B >= 1024 and rest and (rest + 11) // 12 <= sms:
-            fit_kernel = 'smplify_fit_mixed_kernel<16,12> (%d x 16 + %d x 12 samples)' % ((B // (16 * sms)) * sms, (rest + 11) // 12)
+        n16, small, n_small = _native.fit_tile_plan(B, sms)
+        if n16 and n_small:
+            fit_kernel = 'smplify_fit_mixed_kernel<16,%d> (%d x 16 + %d x %d samples)' % (small, n16, n_small, small)
         else:
-            fit_kernel = 'smplify_fit_kernel<%d>' % (16 if B >= 1024 else 8 if B >= 512 else 4)
+            fit_kernel = 'smplify_fit_kernel<%d>' % (16 if n16 else small)
         peaks = measured_peaks()
         fits = world * B * a.steps
         alg_tflops = ALG_GFLOP_PER_FIT * B / (kernel_ms * 1e-3) / 1e3

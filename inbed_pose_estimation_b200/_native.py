@@ -212,6 +212,8 @@ def _declare(lib):
     lib.smplb200_keypoint_3d_loss.argtypes = [ci] + [vp] * 7
     lib.smplb200_shape_loss.restype = ci
     lib.smplb200_shape_loss.argtypes = [ci] + [vp] * 7
+    lib.smplb200_fit_tile_plan.restype = None
+    lib.smplb200_fit_tile_plan.argtypes = [ci, ci] + [ctypes.POINTER(ci)] * 3
     lib.smplb200_smplify_fit_host.restype = ci
     lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
     return lib
@@ -225,7 +227,7 @@ EXPORTED_SYMBOLS = (
     'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count', 'smplb200_probe_fp32_peak',
     'smplb200_rot6d_to_rotmat', 'smplb200_rotmat_to_axis_angle', 'smplb200_estimate_translation', 'smplb200_fits_get',
     'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
-    'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
+    'smplb200_fit_tile_plan', 'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
 )
 
 
@@ -238,6 +240,13 @@ def lib():
                 build()
             _lib = _declare(ctypes.CDLL(LIB_PATH))
         return _lib
+
+
+def fit_tile_plan(batch, sms=148):
+    """(n16, small, n_small): tiles of 16 samples, then n_small tiles of `small` samples (smplb200_fit_tile_plan)."""
+    a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    lib().smplb200_fit_tile_plan(int(batch), int(sms), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return a.value, b.value, c.value
 
 
 def check(rc):

@@ -49,6 +49,13 @@ static int fail(const char* fmt, ...) {
     } while (0)
 
 extern "C" int smplb200_version(void) { return 100; }
+extern "C" void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_small) {
+    int a = 0, b = 0, c = 0;
+    if (batch > 0 && sms > 0) plan_fit_tiles(batch, sms, &a, &b, &c);
+    if (n16) *n16 = a;
+    if (small) *small = b;
+    if (n_small) *n_small = c;
+}
 extern "C" const char* smplb200_last_error(void) { return g_error.c_str(); }
 #if defined(SMPLB200_PHASE_CLOCKS)
 // profiling builds only (tools/phase_clocks.py): read / reset the stage-2 phase cycle counters

@@ -78,49 +78,56 @@ static cudaError_t launch_fit_variant(const ModelView& M, const FitParams& P, cu
     return cudaGetLastError();
 }
 
-// Tile plan of a large batch: n16 tiles of 16 samples followed by n12 tiles of 12.  A wave is one tile per SM, and a
-// 12-sample tile finishes in 0.88 of the time of a 16-sample one (4.89 ms against 5.53 ms, profiles/fit_kernel_r1.md): whole waves of 16s
-// first, then the remainder as one wave of 12s when it fits (at most 12 samples per SM), else as one more wave of 16s.
-void plan_fit_tiles(int batch, int sms, int* n16, int* n12) {
+// Tile plan of a batch: n16 tiles of 16 samples followed by n_small tiles of `small` samples (4, 8 or 12).  A wave is one
+// tile per SM and lasts as long as its tile size dictates (B200, 100 + 100 iterations: 2.6 / 3.5 / 4.7 / 5.3 ms for
+// 4 / 8 / 12 / 16 samples, profiles/fit_kernel_r1.md), so: whole waves of 16s first, then the remainder as ONE wave of the
+// smallest tile size that still covers it (at most `small` samples per SM), else as one more wave of 16s.
+void plan_fit_tiles(int batch, int sms, int* n16, int* small, int* n_small) {
     const int full = batch / (16 * sms);
     const int rest = batch - full * 16 * sms;                    // < 16 * sms
     *n16 = full * sms;
-    *n12 = 0;
+    *small = 0;
+    *n_small = 0;
     if (rest == 0) return;
-    const int t12 = (rest + 11) / 12;
-    if (t12 <= sms) *n12 = t12;
-    else *n16 += (rest + 15) / 16;
+    for (int s = 4; s <= 12; s += 4)
+        if ((rest + s - 1) / s <= sms) { *small = s; *n_small = (rest + s - 1) / s; return; }
+    *n16 += (rest + 15) / 16;
 }
 
-cudaError_t launch_fit_mixed(const ModelView& M, const FitParams& P, int n16, int n12, cudaStream_t stream) {
-    const size_t smem = tile_smem_bytes<16>() > tile_smem_bytes<12>() ? tile_smem_bytes<16>() : tile_smem_bytes<12>();
-    cudaError_t e = opt_in_smem(smplify_fit_mixed_kernel<16, 12>, smem);
+template <int SB>
+static cudaError_t launch_fit_mixed(const ModelView& M, const FitParams& P, int n16, int n_small, cudaStream_t stream) {
+    const size_t smem = tile_smem_bytes<16>() > tile_smem_bytes<SB>() ? tile_smem_bytes<16>() : tile_smem_bytes<SB>();
+    cudaError_t e = opt_in_smem(smplify_fit_mixed_kernel<16, SB>, smem);
     if (e != cudaSuccess) return e;
-    smplify_fit_mixed_kernel<16, 12><<<n16 + n12, kFitThreads, smem, stream>>>(M, P, n16);
+    smplify_fit_mixed_kernel<16, SB><<<n16 + n_small, kFitThreads, smem, stream>>>(M, P, n16);
     return cudaGetLastError();
 }
 
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream) {
     if (P.batch <= 0) return cudaSuccess;
-    static const int variant = [] { const char* v = getenv("SMPLB200_FIT_VARIANT"); return v ? atoi(v) : 0; }();
+    static const int variant = [] { const char* v = getenv("SMPLB200_FIT_VARIANT"); return v ? atoi(v) : 0; }();   // experiments only
     if (variant == 1) return launch_fit_variant<8, 192, 2>(M, P, stream);
     if (variant == 2) return launch_fit_variant<8, 256, 2>(M, P, stream);
     if (variant == 3) return launch_fit_variant<16, 384, 1>(M, P, stream);
     if (variant == 4) return launch_fit_variant<12, 384, 1>(M, P, stream);
-    if (P.batch >= 16 * 64 && variant != 5) {
-        static const int sms = [] {
-            int dev = 0, n = 148;
-            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-            return n > 0 ? n : 148;
-        }();
-        int n16 = 0, n12 = 0;
-        plan_fit_tiles(P.batch, sms, &n16, &n12);
-        if (n12 > 0) return launch_fit_mixed(M, P, n16, n12, stream);
+    if (variant == 6) return launch_fit_variant<8, 384, 1>(M, P, stream);
+    if (variant == 7) return launch_fit_variant<4, 384, 1>(M, P, stream);
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
+    int n16 = 0, small = 0, n_small = 0;
+    plan_fit_tiles(P.batch, sms, &n16, &small, &n_small);
+    if (n16 == 0) {
+        if (small == 4) return launch_fit_variant<4, kFitThreads, 1>(M, P, stream);
+        if (small == 8) return launch_fit_variant<8, kFitThreads, 1>(M, P, stream);
+        return launch_fit_variant<12, kFitThreads, 1>(M, P, stream);
     }
-    // Large batches: 16 samples per CTA amortise the streamed folded basis; small ones: spread over more SMs.
-    if (P.batch >= 16 * 64) return launch_fit_variant<16, kFitThreads, 1>(M, P, stream);
-    if (P.batch >= 8 * 64) return launch_fit_variant<8, kFitThreads, 1>(M, P, stream);
-    return launch_fit_variant<4, kFitThreads, 1>(M, P, stream);
+    if (n_small == 0) return launch_fit_variant<16, kFitThreads, 1>(M, P, stream);
+    if (small == 4) return launch_fit_mixed<4>(M, P, n16, n_small, stream);
+    if (small == 8) return launch_fit_mixed<8>(M, P, n16, n_small, stream);
+    return launch_fit_mixed<12>(M, P, n16, n_small, stream);
 }
 
 template <int S>

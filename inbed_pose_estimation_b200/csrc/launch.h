@@ -12,6 +12,7 @@ constexpr int kFitThreads = 384;
 constexpr int kPoseThreads = 384;
 
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream);
+void plan_fit_tiles(int batch, int sms, int* n16, int* small, int* n_small);
 cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
 cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
 cudaError_t launch_quat_rodrigues_fwd(const float* theta, float* rot, int n, cudaStream_t st);

@@ -200,6 +200,10 @@ int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_it
                               float* vertices, float* joints, float* pose, float* betas, float* camera_translation,
                               float* reprojection_loss);
 
+/* How smplb200_smplify_fit tiles a batch over `sms` SMs (one CTA per tile, one tile per SM and wave): n16 tiles of 16
+ * samples followed by n_small tiles of `small` (4, 8 or 12; 0 = none) samples.  Pure host arithmetic. */
+void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_small);
+
 /* Number of this library's kernel launches issued by the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long long smplb200_launch_count(int reset);

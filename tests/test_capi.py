@@ -53,3 +53,23 @@ def test_host_side_validation():
         geometry.batch_rodrigues(torch.zeros(3, 3))
     with pytest.raises(RuntimeError, match='CUDA'):
         geometry.perspective_projection(torch.zeros(1, 2, 3), torch.eye(3)[None], torch.zeros(1, 3), 5000., torch.zeros(1, 2))
+
+
+def test_fit_tile_plan_covers_every_batch_in_the_fewest_waves():
+    """smplb200_fit_tile_plan: host arithmetic behind the fit launch (no GPU).  Every sample is covered, the 16-sample tiles
+    form whole waves, the remainder is one wave of the smallest tile size that holds it."""
+    sms = 148
+    for batch in list(range(1, 70)) + [255, 256, 592, 593, 1184, 1185, 1776, 1777, 2368, 2369, 4096, 4103, 4736, 65536, 100000]:
+        n16, small, n_small = _native.fit_tile_plan(batch, sms)
+        assert n16 * 16 + n_small * small >= batch
+        assert n16 * 16 + max(n_small - 1, 0) * small < batch or n_small == 0 and (n16 - 1) * 16 < batch     # no empty tile
+        assert small in (0, 4, 8, 12) and (n_small == 0) == (small == 0)
+        assert 0 <= n_small <= sms
+        if n_small:
+            assert n16 % sms == 0                                            # whole waves of 16s before the small tiles
+            rest = batch - n16 * 16
+            assert all((rest + s - 1) // s > sms for s in (4, 8, 12) if s < small)      # no smaller size would fit one wave
+    assert _native.fit_tile_plan(4096, sms) == (148, 12, 144)
+    assert _native.fit_tile_plan(32, sms) == (0, 4, 8)
+    assert _native.fit_tile_plan(4736, sms) == (296, 0, 0)
+    assert _native.fit_tile_plan(0, sms) == (0, 0, 0)
