@@ -10,8 +10,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, 'inbed_pose_estimation_b200', 'libsmplify_b200_clk.so')
-NAMES = ['prior_quadratic', 'prior_select', 'pose_features+rest_joints', 'chain_forward', 'fold_gemm_forward', 'output_joints',
-         'reprojection(+trace)', 'joint_backward', 'pick_backward', 'fold_gemm_backward', 'chain_backward', 'rodrigues_bwd+adam']
+NAMES = ['prior GEMM', 'prior select + angle/shape priors', 'Rodrigues + pose features + rest joints', '(mark)',
+         'folded GEMM forward || chain forward', '49 output joints', 'projection + GMoF (+ trace)', 'source grads + joint backward',
+         'picked-vertex backward', '(mark)', 'folded GEMM backward || chain backward', 'Rodrigues backward + Adam']
 
 if sys.argv[1] == 'build':
     from inbed_pose_estimation_b200 import _native
@@ -39,4 +40,4 @@ else:
     tot = sum(buf[i] for i in range(12))
     print('stage-2 cycles per iteration (CTA 0): %.0f' % (tot / a.iters))
     for i, n in enumerate(NAMES):
-        print('%-28s %9.0f clk/iter  %5.1f%%' % (n, buf[i] / a.iters, 100.0 * buf[i] / tot))
+        print('%-42s %9.0f clk/iter  %5.1f%%' % (n, buf[i] / a.iters, 100.0 * buf[i] / tot))
