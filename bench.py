@@ -100,6 +100,22 @@ def time_oracle_cpu(batch_sample, steps, warmup):
     return batch_sample * steps / dt, dt / steps, cores
 
 
+def time_oracle_cpu_smpl_forward(pose, betas, reps=5):
+    """CPU baseline of BASELINE config 1 (SMPL forward, batch 32): the oracle port on all host threads -> (ms per call, cores).
+    Lives here because bench.py's cpu_baseline leg is the one place outside tests/ that may execute oracle/."""
+    import torch
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle = port.build_oracle(seed=0, num_iters=1)
+    with torch.no_grad():
+        oracle.smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            oracle.smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
+    return (time.perf_counter() - t0) / reps * 1e3, cores
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:

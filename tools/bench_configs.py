@@ -68,17 +68,9 @@ def main():
             ms = cuda_time(lambda: smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas), a.reps)
         line = {'config': 1, 'workload': 'SMPL forward (LBS) batch 32 fp32', 'gpu_ms': ms, 'gpu_bodies_per_s': 32 / ms * 1e3}
         if not a.no_cpu:
-            from oracle import port
-            oracle = port.build_oracle(seed=0, num_iters=1)
-            torch.set_num_threads(os.cpu_count() or 1)
-            pc, bc = pose.cpu(), betas.cpu()
-            with torch.no_grad():
-                oracle.smpl(global_orient=pc[:, :3], body_pose=pc[:, 3:], betas=bc)
-                t0 = time.perf_counter()
-                for _ in range(5):
-                    oracle.smpl(global_orient=pc[:, :3], body_pose=pc[:, 3:], betas=bc)
-                cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
-            line.update({'cpu_ms': cpu_ms, 'cpu_bodies_per_s': 32 / cpu_ms * 1e3, 'cpu_cores': os.cpu_count(), 'cpu_kind': 'port'})
+            import bench                                   # the CPU baseline leg lives in bench.py
+            cpu_ms, cores = bench.time_oracle_cpu_smpl_forward(pose.cpu(), betas.cpu())
+            line.update({'cpu_ms': cpu_ms, 'cpu_bodies_per_s': 32 / cpu_ms * 1e3, 'cpu_cores': cores, 'cpu_kind': 'port'})
         out.append(line)
 
     if 2 in want and rank == 0:
