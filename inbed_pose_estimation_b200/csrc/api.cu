@@ -148,18 +148,18 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // Device workspace.  The pose kernels write the per-sample operands of the tcgen05 vertex kernels (x hi/lo [B][224],
 // skinning transforms hi/lo [B][12][32]); `big0` holds v_posed [B][20736] in forward calls without a caller-supplied
-// saved buffer and dvp_hi in backward calls, `big1` dvp_lo and `big2` the padded copy of dverts (backward only), then
+// saved buffer and dvp (fp32) in backward calls, `big2` the padded copy of dverts (backward only), then
 // the per-split partial sums.
 struct Work {
     TcOperands tc;
-    float *big0, *big1, *big2, *dA, *dx;
+    float *big0, *big2, *dA, *dx;
 };
 static size_t big_bytes(int batch) { return align256((size_t)batch * kVpPitch * 4); }
 static size_t work_bytes(int batch, bool with_backward) {
     const size_t x = align256((size_t)batch * kXPad * 4), ae = align256((size_t)batch * kAeRow * 4);
     size_t n = 2 * x + 2 * ae + big_bytes(batch) + 256;
     if (with_backward)
-        n += 2 * big_bytes(batch) + (size_t)kMaxSplitA * align256((size_t)batch * 288 * 4) + (size_t)kMaxSplitX * x;
+        n += big_bytes(batch) + (size_t)kMaxSplitA * align256((size_t)batch * 288 * 4) + (size_t)kMaxSplitX * x;
     return n;
 }
 static Work carve(void* ws, int batch) {
@@ -171,8 +171,7 @@ static Work carve(void* ws, int batch) {
     k.tc.ae_hi = reinterpret_cast<float*>(w); w += ae;
     k.tc.ae_lo = reinterpret_cast<float*>(w); w += ae;
     k.big0 = reinterpret_cast<float*>(w); w += big_bytes(batch);
-    k.big1 = reinterpret_cast<float*>(w); w += big_bytes(batch);          // backward workspaces only (from here on)
-    k.big2 = reinterpret_cast<float*>(w); w += big_bytes(batch);
+    k.big2 = reinterpret_cast<float*>(w); w += big_bytes(batch);          // backward workspaces only (from here on)
     k.dA = reinterpret_cast<float*>(w); w += (size_t)kMaxSplitA * align256((size_t)batch * 288 * 4);
     k.dx = reinterpret_cast<float*>(w);
     return k;
@@ -289,8 +288,8 @@ extern "C" int smplb200_smpl_backward(const smplb200_model* m, int batch, int ro
         F.tc.x_hi = nullptr; F.tc.x_lo = nullptr;
         CUDA_OK(launch_pose_forward(m->view, F, st));
         const int nsa = tc_dA_splits(batch), nsx = tc_dx_splits(batch);
-        CUDA_OK(launch_skin_backward(m->tc_maps, wk.tc.ae_hi, wk.tc.ae_lo, grad_vertices, wk.big0, wk.big1, wk.big2, batch, st));
-        CUDA_OK(launch_dx_gemm(m->tc_maps, wk.big0, wk.big1, wk.dx, batch, nsx, st));
+        CUDA_OK(launch_skin_backward(m->tc_maps, wk.tc.ae_hi, wk.tc.ae_lo, grad_vertices, wk.big0, wk.big2, batch, st));
+        CUDA_OK(launch_dx_gemm(m->tc_maps, wk.big0, wk.dx, batch, nsx, st));
         CUDA_OK(launch_dA(m->tc_maps, wk.big2, saved_vposed, wk.dA, batch, nsa, st));
         g_launches += 4;
         P.dA_part = wk.dA; P.dx_part = wk.dx; P.nsplit_a = nsa; P.nsplit_x = nsx;

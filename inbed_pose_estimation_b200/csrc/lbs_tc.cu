@@ -43,6 +43,12 @@ struct Barrier { uint64_t v; };
 // SPLITK = true: one (m tile, K range) item per CTA, chains of CHAIN k-blocks alternate between two TMEM buffers and are
 // added into fp32 registers by the flush warps; the partial result is written with plain stores.
 // =====================================================================================================================
+// hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 container), lo = x - hi (exact)
+__device__ __forceinline__ void split_trunc(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
 struct alignas(64) GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, out; };
 struct GemmWork {
     int num_items;      // m tiles * n tiles * nsplit
@@ -65,6 +71,7 @@ struct GemmSmem {
 };
 struct GemmBars {
     uint64_t full[2], empty[2], tmem_full[2], tmem_empty[2];
+    uint64_t split[2];          // SPLITK: the consumer warps have produced the lo half of the stage's A operand
     uint32_t tmem_base;
 };
 
@@ -83,8 +90,9 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), CONSUMER_WARPS); }
+        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars->split[i]), CONSUMER_WARPS);
         fence_barrier_init();
-        prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_hi); prefetch_tmap(&maps.b_lo);
+        prefetch_tmap(&maps.a_hi); if (!SPLITK) prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_hi); prefetch_tmap(&maps.b_lo);
         if (!SPLITK) prefetch_tmap(&maps.out);
     }
     if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
@@ -113,9 +121,10 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
                     mbar_wait(smem_u32(&bars->empty[r.stage]), r.phase ^ 1);
                     const uint32_t full = smem_u32(&bars->full[r.stage]);
                     const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
-                    mbar_expect_tx(full, SM::STAGE_BYTES);
+                    // SPLITK: the A operand arrives as plain fp32 (maps.a_hi) and is split into hi / lo on chip
+                    mbar_expect_tx(full, SPLITK ? SM::STAGE_BYTES - TILE128 : SM::STAGE_BYTES);
                     tma_load_2d(base, &maps.a_hi, full, kb * BK, mt * BM);
-                    tma_load_2d(base + TILE128, &maps.a_lo, full, kb * BK, mt * BM);
+                    if (!SPLITK) tma_load_2d(base + TILE128, &maps.a_lo, full, kb * BK, mt * BM);
                     tma_load_2d(base + 2 * TILE128, &maps.b_hi, full, kb * BK, nt * NT);
                     tma_load_2d(base + 2 * TILE128 + SM::B_BYTES, &maps.b_lo, full, kb * BK, nt * NT);
                     r.advance();
@@ -136,7 +145,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
                 tc_fence_after();
                 const uint32_t tm = tmem_base + t.stage * NT;
                 for (int kb = g0; kb < g1; ++kb) {
-                    mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
+                    mbar_wait(smem_u32(SPLITK ? &bars->split[r.stage] : &bars->full[r.stage]), r.phase);
                     tc_fence_after();
                     const uint32_t base = s_base + r.stage * SM::STAGE_BYTES;
                     const uint64_t d_ah = smem_desc(base), d_al = smem_desc(base + TILE128);
@@ -202,29 +211,61 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
             constexpr int HALF = NT / 2;                      // columns per flush warp (two warps share a lane quarter)
             static_assert(HALF % 16 == 0, "flush width");
             const int half = (warp - 4) >> 2;
+            const int ctid = threadIdx.x - 128;               // 0..255 over the 8 consumer warps
             float acc[HALF];
 #pragma unroll
             for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+            Ring<STAGES> r;
+            // add one finished accumulation chain (TMEM buffer tq) into the fp32 registers and hand the buffer back
+            auto flush = [&](const Ring<2>& tq) {
+                mbar_wait(smem_u32(&bars->tmem_full[tq.stage]), tq.phase);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + lane_bits + tq.stage * NT + half * HALF;
+#pragma unroll
+                for (int c = 0; c < HALF / 8; ++c) {
+                    float v[8];
+                    tmem_ld8(ta + 8 * c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[8 * c + i] += v[i];
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[tq.stage]));
+            };
             for (int item = blockIdx.x; item < work.num_items; item += gridDim.x) {       // one item per CTA in practice
                 int mt, nt, sp, kb0, kb1;
                 decode(item, mt, nt, sp, kb0, kb1);
+                bool pending = false;
+                Ring<2> prev;
                 for (int g0 = kb0; g0 < kb1; g0 += work.chain) {
-                    mbar_wait(smem_u32(&bars->tmem_full[t.stage]), t.phase);
-                    tc_fence_after();
-                    const uint32_t ta = tmem_base + lane_bits + t.stage * NT + half * HALF;
+                    const int g1 = (g0 + work.chain < kb1) ? g0 + work.chain : kb1;
+                    for (int kb = g0; kb < g1; ++kb) {
+                        // split the k-block's fp32 A tile (128 rows x 32 floats, swizzled as TMA wrote it) element-wise, in
+                        // place: hi = the 19 bits the tensor core reads, lo = x - hi (exact) into the stage's second tile
+                        mbar_wait(smem_u32(&bars->full[r.stage]), r.phase);
+                        float4* hi4 = reinterpret_cast<float4*>(smem + r.stage * SM::STAGE_BYTES);
+                        float4* lo4 = reinterpret_cast<float4*>(smem + r.stage * SM::STAGE_BYTES + TILE128);
 #pragma unroll
-                    for (int c = 0; c < HALF / 8; ++c) {
-                        float v[8];
-                        tmem_ld8(ta + 8 * c, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[8 * c + i] += v[i];
+                        for (int i = 0; i < (int)(TILE128 / 16) / 256; ++i) {
+                            const float4 x = hi4[i * 256 + ctid];
+                            float4 h, l;
+                            split_trunc(x.x, h.x, l.x); split_trunc(x.y, h.y, l.y); split_trunc(x.z, h.z, l.z); split_trunc(x.w, h.w, l.w);
+                            hi4[i * 256 + ctid] = h;
+                            lo4[i * 256 + ctid] = l;
+                        }
+                        fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core's async proxy
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&bars->split[r.stage]));
+                        r.advance();
+                        // the previous chain is flushed one k-block late: its MMAs have long finished, nothing waits
+                        if (kb == g0 && pending) { flush(prev); pending = false; }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[t.stage]));
+                    prev = t;
+                    pending = true;
                     t.advance();
                 }
+                if (pending) flush(prev);
                 const int b = mt * BM + row;
                 if (b < batch) {
                     float4* o = reinterpret_cast<float4*>(out_direct + ((size_t)sp * batch + b) * NT + half * HALF);
@@ -397,17 +438,11 @@ tc_skin_kernel(const __grid_constant__ SkinMaps maps, const float* __restrict__ 
                         }
                     } else {
                         if (b < batch) {                                 // padded vertices get zeros (dverts masked above)
-                            float* oh = out0 + (size_t)b * kVpPitch + 3 * v;
-                            float* ol = out1 + (size_t)b * kVpPitch + 3 * v;
+                            float* od = out0 + (size_t)b * kVpPitch + 3 * v;     // dvp in fp32: the dx GEMM splits it on chip
                             float* oc = out2 + (size_t)b * kVpPitch + 3 * v;     // 16-byte aligned copy of dverts for the dA kernel's TMA
                             oc[0] = a0; oc[1] = a1; oc[2] = a2;
 #pragma unroll
-                            for (int cc = 0; cc < 3; ++cc) {
-                                const float d = Tt[cc] * a0 + Tt[4 + cc] * a1 + Tt[8 + cc] * a2;
-                                const float hi = tf32_round(d);
-                                oh[cc] = hi;
-                                ol[cc] = d - hi;
-                            }
+                            for (int cc = 0; cc < 3; ++cc) od[cc] = Tt[cc] * a0 + Tt[4 + cc] * a1 + Tt[8 + cc] * a2;
                         }
                     }
                 }
@@ -452,11 +487,7 @@ struct DaBars {
     uint32_t tmem_base;
 };
 
-// hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 container), lo = x - hi (exact)
-__device__ __forceinline__ void split_trunc(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
-}
+
 
 __global__ void __launch_bounds__(384, 1)
 tc_dA_kernel(const __grid_constant__ DaMaps maps, float* __restrict__ dA_part, int batch, int nsplit) {
@@ -710,15 +741,14 @@ int tc_dx_splits(int batch) {
     return best;
 }
 
-cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const float* dvp_lo, float* dx_part, int batch, int nsplit,
-                           cudaStream_t stream) {
+cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp, float* dx_part, int batch, int nsplit, cudaStream_t stream) {
     if (batch <= 0) return cudaSuccess;
     constexpr int NT = 224;
     tc::GemmMaps maps;
     maps.b_hi = cm.bm_hi;
     maps.b_lo = cm.bm_lo;
-    if (!make_map(&maps.a_hi, dvp_hi, kVpPitch, (uint64_t)batch, 0, tc::BM) || !make_map(&maps.a_lo, dvp_lo, kVpPitch, (uint64_t)batch, 0, tc::BM))
-        return cudaErrorInvalidValue;
+    if (!make_map(&maps.a_hi, dvp, kVpPitch, (uint64_t)batch, 0, tc::BM)) return cudaErrorInvalidValue;
+    maps.a_lo = maps.a_hi;               // the split-K kernel derives the lo half on chip
     maps.out = maps.a_hi;                // unused by the split-K epilogue
     tc::GemmWork w;
     const int mtiles = (batch + tc::BM - 1) / tc::BM;
@@ -757,9 +787,9 @@ cudaError_t launch_skin_forward(const TcConstMaps& cm, const float* ae_hi, const
                                 int batch, cudaStream_t stream) {
     return launch_skin(0, cm, ae_hi, ae_lo, vposed, verts, nullptr, nullptr, batch, stream);
 }
-cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp_hi,
-                                 float* dvp_lo, float* dverts_padded, int batch, cudaStream_t stream) {
-    return launch_skin(1, cm, ae_hi, ae_lo, dverts, dvp_hi, dvp_lo, dverts_padded, batch, stream);
+cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp,
+                                 float* dverts_padded, int batch, cudaStream_t stream) {
+    return launch_skin(1, cm, ae_hi, ae_lo, dverts, dvp, nullptr, dverts_padded, batch, stream);
 }
 
 int tc_dA_splits(int batch) {

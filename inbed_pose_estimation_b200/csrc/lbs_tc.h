@@ -35,13 +35,13 @@ cudaError_t launch_blend_gemm(const TcConstMaps& cm, const float* x_hi, const fl
 // verts[b][v] = (W . A_b)[v] [v_posed[b][v]; 1]      (tcgen05 skinning GEMM, M = vertices, N = (sample, entry), K = 24)
 cudaError_t launch_skin_forward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* vposed, float* verts,
                                 int batch, cudaStream_t stream);
-// dvp[b][v] = (W . A_b)[v]^R^T dverts[b][v], written as hi / lo tf32 parts [B][20736]; also copies dverts into the padded,
-// 16-byte aligned layout [B][20736] the dA kernel's TMA loads need (the caller's [B][6890][3] rows are only 8-byte aligned)
-cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp_hi,
-                                 float* dvp_lo, float* dverts_padded, int batch, cudaStream_t stream);
-// dx_part[split][B][224] = dvp . basis^T over the split's K range   (tcgen05, K = 20736 split nsplit ways)
-cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp_hi, const float* dvp_lo, float* dx_part, int batch, int nsplit,
-                           cudaStream_t stream);
+// dvp[b][v] = (W . A_b)[v]^R^T dverts[b][v], written in fp32 [B][20736]; also copies dverts into the padded, 16-byte aligned
+// layout [B][20736] the dA kernel's TMA loads need (the caller's [B][6890][3] rows are only 8-byte aligned)
+cudaError_t launch_skin_backward(const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* dverts, float* dvp,
+                                 float* dverts_padded, int batch, cudaStream_t stream);
+// dx_part[split][B][224] = dvp . basis^T over the split's K range   (tcgen05, K = 20736 split nsplit ways; dvp is split
+// into its tf32 hi / lo parts on chip)
+cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp, float* dx_part, int batch, int nsplit, cudaStream_t stream);
 // dA_part[split][B][12][24] = sum_v W[v][j] dverts[b][v][r] [v_posed[b][v]; 1][c]   (tcgen05, operands generated on chip)
 cudaError_t launch_dA(const TcConstMaps& cm, const float* dverts_padded, const float* vposed, float* dA_part, int batch, int nsplit,
                       cudaStream_t stream);
