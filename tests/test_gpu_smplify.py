@@ -111,3 +111,22 @@ def test_empty_batch_and_errors(fitter):
         fitter(z(2, 72), z(2, 10), z(2, 3), z(2, 2), z(2, 48, 3))
     with pytest.raises(RuntimeError, match='CUDA'):
         fitter(torch.zeros(2, 72), z(2, 10), z(2, 3), z(2, 2), z(2, 49, 3))
+
+
+@pytest.mark.parametrize('B,small', [(16 * 148 + 30, 4), (16 * 148 + 700, 8), (16 * 148 + 1300, 12), (12 * 148 - 5, 12), (8 * 148, 8)])
+def test_every_tile_mix_gives_the_same_fits(B, small):
+    """The tile plan (16-sample waves + one wave of 4-, 8- or 12-sample tiles) only changes where a sample is computed:
+    rows of the remainder wave and of the first wave equal the same rows fitted alone (4-sample tiles)."""
+    from inbed_pose_estimation_b200 import _native
+    n16, s, n_small = _native.fit_tile_plan(B, torch.cuda.get_device_properties(0).multi_processor_count)
+    if torch.cuda.get_device_properties(0).multi_processor_count == 148:
+        assert s == small
+    fitter5 = synthetic.build_smplify('cuda', num_iters=5, seed=0)
+    inp = synthetic.make_fit_inputs(B, seed=B)
+    out = fitter5(*_cuda(inp))
+    assert all(torch.isfinite(t).all() for t in out)
+    for lo, hi in ((3, 29), (B - 37, B)):
+        sub = {k: v[lo:hi] for k, v in inp.items()}
+        out_sub = fitter5(*_cuda(sub))
+        for a, b in zip(out, out_sub):
+            np.testing.assert_allclose(a[lo:hi].cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-4)
