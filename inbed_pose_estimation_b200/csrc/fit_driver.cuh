@@ -438,13 +438,13 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
         sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
     }
     FOR_ITEMS(it, S * 288) {
-        const int s = it / 288, k = it % 288, b = first + s;
+        // k runs in the partials' own (entry-major) order so that a warp reads 128 contiguous bytes per split
+        const int s = it / 288, k = it % 288, b = first + s, e = k / kJoints, j = k % kJoints;
         float a = 0.f;
         if (P.dA_part && b < P.batch) {
-            const int j = k / 12, e = k % 12;
-            for (int sp = 0; sp < P.nsplit_a; ++sp) a += P.dA_part[(((size_t)sp * P.batch + b) * 12 + e) * kJoints + j];
+            for (int sp = 0; sp < P.nsplit_a; ++sp) a += P.dA_part[((size_t)sp * P.batch + b) * 288 + k];
         }
-        sm[L::DG + k * S + s] = a;
+        sm[L::DG + (j * 12 + e) * S + s] = a;
     }
     TILE_SYNC();
     ph_joint_backward<S>(M, C, sm);
