@@ -49,7 +49,7 @@ __device__ __forceinline__ void split_trunc(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-struct alignas(64) GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, out; };
+struct alignas(64) GemmMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, out, bh_half, bl_half; };    // *_half: box of NT / 2 rows (cluster multicast)
 struct GemmWork {
     int num_items;      // m tiles * n tiles * nsplit
     int n_tiles;        // N tiles per m tile
@@ -67,6 +67,7 @@ struct GemmSmem {
     static constexpr uint32_t OFF_BAR = OFF_OUT + 2 * TILE128;
     static constexpr uint32_t BYTES = OFF_BAR + 256 + 1024;            // + barriers + alignment slack
     static_assert(B_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned");
+    static_assert((B_BYTES / 2) % 1024 == 0 || NT % 16 != 0, "half tiles (cluster multicast) must stay 1024-byte aligned");
     static_assert(BYTES <= 232448, "shared memory budget");
 };
 struct GemmBars {
@@ -75,9 +76,12 @@ struct GemmBars {
     uint32_t tmem_base;
 };
 
-template <int NT, bool SPLITK>
+// CL = 2 (SPLITK only): the two CTAs of a cluster take neighbouring m tiles of the same K range; each fetches half of every
+// B (basis) tile and multicasts it to both, so the hi / lo basis - the bulk of the operand bytes - leaves L2 once per pair.
+template <int NT, bool SPLITK, int CL = 1>
 __global__ void __launch_bounds__(SPLITK ? 384 : 256, 1)
 tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float* __restrict__ out_direct, int batch) {
+    static_assert(CL == 1 || (CL == 2 && SPLITK), "clusters are used by the split-K kernel only");
     using SM = GemmSmem<NT>;
     constexpr int STAGES = SM::STAGES;
     constexpr int CONSUMER_WARPS = SPLITK ? 8 : 4;
@@ -88,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), CONSUMER_WARPS); }
         for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars->split[i]), CONSUMER_WARPS);
         fence_barrier_init();
@@ -98,14 +102,17 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
     if (warp == 2) tmem_alloc<512>(smem_u32(&bars->tmem_base));
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
 
     auto decode = [&](int item, int& mt, int& nt, int& sp, int& kb0, int& kb1) {
+        if (CL > 1) item /= CL;                      // the CTAs of a cluster share the item and take m tiles CL * t + rank
         sp = item % work.nsplit;
         const int t = item / work.nsplit;
         nt = t % work.n_tiles;
-        mt = t / work.n_tiles;
+        mt = (t / work.n_tiles) * CL + (int)crank;
         kb0 = (int)(((long long)work.total_kb * sp) / work.nsplit);
         kb1 = (int)(((long long)work.total_kb * (sp + 1)) / work.nsplit);
     };
@@ -125,8 +132,15 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
                     mbar_expect_tx(full, SPLITK ? SM::STAGE_BYTES - TILE128 : SM::STAGE_BYTES);
                     tma_load_2d(base, &maps.a_hi, full, kb * BK, mt * BM);
                     if (!SPLITK) tma_load_2d(base + TILE128, &maps.a_lo, full, kb * BK, mt * BM);
-                    tma_load_2d(base + 2 * TILE128, &maps.b_hi, full, kb * BK, nt * NT);
-                    tma_load_2d(base + 2 * TILE128 + SM::B_BYTES, &maps.b_lo, full, kb * BK, nt * NT);
+                    if (CL == 1) {
+                        tma_load_2d(base + 2 * TILE128, &maps.b_hi, full, kb * BK, nt * NT);
+                        tma_load_2d(base + 2 * TILE128 + SM::B_BYTES, &maps.b_lo, full, kb * BK, nt * NT);
+                    } else {
+                        // this CTA's half of the B rows, delivered to both CTAs (each full barrier still sees the whole tile)
+                        const uint32_t hoff = crank * (SM::B_BYTES / 2);
+                        tma_load_2d_mc(base + 2 * TILE128 + hoff, &maps.bh_half, full, kb * BK, nt * NT + (int)crank * (NT / 2), 0x3);
+                        tma_load_2d_mc(base + 2 * TILE128 + SM::B_BYTES + hoff, &maps.bl_half, full, kb * BK, nt * NT + (int)crank * (NT / 2), 0x3);
+                    }
                     r.advance();
                 }
             }
@@ -158,7 +172,8 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
                             umma_tf32(tm, d_al + ko, d_bh + ko, idesc, 1);
                             umma_tf32(tm, d_ah + ko, d_bl + ko, idesc, 1);
                         }
-                        umma_commit(smem_u32(&bars->empty[r.stage]));
+                        if (CL == 1) umma_commit(smem_u32(&bars->empty[r.stage]));
+                        else umma_commit_mc(smem_u32(&bars->empty[r.stage]), 0x3);     // the stage is free when BOTH CTAs have read it
                     }
                     __syncwarp();
                     r.advance();
@@ -279,6 +294,7 @@ tc_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmWork work, float
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // no CTA leaves while its peer may still multicast to it or arrive on its barriers
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -685,6 +701,7 @@ bool tc_make_constant_maps(TcConstMaps* m, const float* basisT_hi, const float* 
                            const float* basis_lo, const float* w_hi, const float* w_lo, const float* wT_hi, const float* wT_lo) {
     return make_map(&m->bT_hi, basisT_hi, kXPad, kColsPad, 0, 256) && make_map(&m->bT_lo, basisT_lo, kXPad, kColsPad, 0, 256) &&
            make_map(&m->bm_hi, basis_hi, kColsPad, kXPad, 0, 224) && make_map(&m->bm_lo, basis_lo, kColsPad, kXPad, 0, 224) &&
+           make_map(&m->bm_hi_half, basis_hi, kColsPad, kXPad, 0, 112) && make_map(&m->bm_lo_half, basis_lo, kColsPad, kXPad, 0, 112) &&
            make_map(&m->w_hi, w_hi, 32, kTcVertRowsPad, 0, 128) && make_map(&m->w_lo, w_lo, 32, kTcVertRowsPad, 0, 128) &&
            make_map(&m->wT_hi, wT_hi, kTcVertRowsPad, 32, 0, 32) && make_map(&m->wT_lo, wT_lo, kTcVertRowsPad, 32, 0, 32);
 }
@@ -747,6 +764,8 @@ cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp, float* dx_pa
     tc::GemmMaps maps;
     maps.b_hi = cm.bm_hi;
     maps.b_lo = cm.bm_lo;
+    maps.bh_half = cm.bm_hi_half;
+    maps.bl_half = cm.bm_lo_half;
     if (!make_map(&maps.a_hi, dvp, kVpPitch, (uint64_t)batch, 0, tc::BM)) return cudaErrorInvalidValue;
     maps.a_lo = maps.a_hi;               // the split-K kernel derives the lo half on chip
     maps.out = maps.a_hi;                // unused by the split-K epilogue
@@ -756,11 +775,36 @@ cudaError_t launch_dx_gemm(const TcConstMaps& cm, const float* dvp, float* dx_pa
     w.nsplit = nsplit;
     w.total_kb = kVpPitch / tc::BK;      // 648
     w.chain = 7;                          // 84 MMAs per accumulation chain
-    w.num_items = mtiles * nsplit;
-    cudaError_t e = opt_in(tc::tc_gemm_kernel<NT, true>, tc::GemmSmem<NT>::BYTES);
+    static const bool no_cluster = getenv("SMPLB200_DX_NOCLUSTER") != nullptr;          // experiments only
+    auto launch_single = [&]() -> cudaError_t {
+        w.num_items = mtiles * nsplit;
+        cudaError_t e = opt_in(tc::tc_gemm_kernel<NT, true, 1>, tc::GemmSmem<NT>::BYTES);
+        if (e != cudaSuccess) return e;
+        tc::tc_gemm_kernel<NT, true, 1><<<w.num_items, 384, tc::GemmSmem<NT>::BYTES, stream>>>(maps, w, dx_part, batch);
+        return cudaGetLastError();
+    };
+    if (mtiles < 2 || no_cluster) return launch_single();
+    // pairs of m tiles share the basis tiles through a 2-CTA cluster (an odd last tile is paired with an all-padding one)
+    const int mpairs = (mtiles + 1) / 2;
+    w.num_items = mpairs * nsplit * 2;
+    cudaError_t e = opt_in(tc::tc_gemm_kernel<NT, true, 2>, tc::GemmSmem<NT>::BYTES);
     if (e != cudaSuccess) return e;
-    tc::tc_gemm_kernel<NT, true><<<w.num_items, 384, tc::GemmSmem<NT>::BYTES, stream>>>(maps, w, dx_part, batch);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)w.num_items);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = tc::GemmSmem<NT>::BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, tc::tc_gemm_kernel<NT, true, 2>, maps, w, dx_part, batch);
+    if (e == cudaSuccess) return e;
+    (void)cudaGetLastError();            // a device that cannot place CTA pairs (partitioned GPU): same kernel without the cluster
+    return launch_single();
 }
 
 static cudaError_t launch_skin(int mode, const TcConstMaps& cm, const float* ae_hi, const float* ae_lo, const float* in, float* out0,

@@ -16,6 +16,7 @@ constexpr int kMaxSplitX = 16;              // K splits of the dx GEMM
 struct alignas(64) TcConstMaps {  // TMA tensor maps of the immutable model operands (hi / lo tf32 parts)
     CUtensorMap bT_hi, bT_lo;     // basis^T [20736][224]  box 256 x 32   B operand of the blend-shape GEMM
     CUtensorMap bm_hi, bm_lo;     // basis   [224][20736]  box 224 x 32   B operand of the dx GEMM
+    CUtensorMap bm_hi_half, bm_lo_half;   // same tensors, box 112 x 32: the half tile one CTA of a cluster pair multicasts
     CUtensorMap w_hi, w_lo;       // W       [6912][32]    box 128 x 32   A operand of the skinning GEMM
     CUtensorMap wT_hi, wT_lo;     // W^T     [32][6912]    box  32 x 32   B operand of the dA GEMM
 };
