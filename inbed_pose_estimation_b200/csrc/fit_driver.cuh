@@ -393,6 +393,22 @@ struct PoseParams {
     float* d_betas;           // [B][10]
 };
 
+// p[0] + p[stride] + ... (n terms of four floats, in that order; p 16-byte aligned, stride a multiple of 4).  Eight loads are
+// issued before the first add: the partials come from HBM and a dependent load-add chain would pay the full memory latency
+// per split.
+SB_HD float4 sum_partials4(const float* p, size_t stride, int n) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v[u] = (i0 + u < n) ? *reinterpret_cast<const float4*>(p + (size_t)(i0 + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    }
+    return a;
+}
+
 template <int S>
 SB_HD void pose_load(const PoseParams& P, int first, float* sm) {
     using L = TileLayout<S>;
@@ -437,14 +453,18 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
         const int s = it / 147, k = it % 147, b = first + s;
         sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
     }
-    FOR_ITEMS(it, S * 288) {
-        // k runs in the partials' own (entry-major) order so that a warp reads 128 contiguous bytes per split
-        const int s = it / 288, k = it % 288, b = first + s, e = k / kJoints, j = k % kJoints;
-        float a = 0.f;
-        if (P.dA_part && b < P.batch) {
-            for (int sp = 0; sp < P.nsplit_a; ++sp) a += P.dA_part[((size_t)sp * P.batch + b) * 288 + k];
+    FOR_ITEMS(it, S * 72) {
+        // four consecutive entries of the partials' own (entry-major [12][24]) order per item: 16-byte loads, a warp reads
+        // 512 contiguous bytes per split, eight splits in flight
+        const int s = it / 72, k4 = it % 72, b = first + s;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.dA_part && b < P.batch) a = sum_partials4(P.dA_part + (size_t)b * 288 + 4 * k4, (size_t)P.batch * 288, P.nsplit_a);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = 4 * k4 + u, e = k / kJoints, j = k % kJoints;
+            sm[L::DG + (j * 12 + e) * S + s] = av[u];
         }
-        sm[L::DG + (j * 12 + e) * S + s] = a;
     }
     TILE_SYNC();
     ph_joint_backward<S>(M, C, sm);
@@ -453,12 +473,14 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
     TILE_SYNC();
     ph_gemm_and_chain_backward<S>(M, sm);
     if (P.dx_part) {
-        FOR_ITEMS(it, S * kXPad) {
-            const int s = it / kXPad, k = it % kXPad, b = first + s;
+        FOR_ITEMS(it, S * (kXPad / 4)) {
+            const int s = it / (kXPad / 4), k4 = it % (kXPad / 4), b = first + s;
             if (b < P.batch) {
-                float a = sm[L::XT + k * S + s];
-                for (int sp = 0; sp < P.nsplit_x; ++sp) a += P.dx_part[((size_t)sp * P.batch + b) * kXPad + k];
-                sm[L::XT + k * S + s] = a;
+                const float4 a = sum_partials4(P.dx_part + (size_t)b * kXPad + 4 * k4, (size_t)P.batch * kXPad, P.nsplit_x);
+                sm[L::XT + (4 * k4 + 0) * S + s] += a.x;
+                sm[L::XT + (4 * k4 + 1) * S + s] += a.y;
+                sm[L::XT + (4 * k4 + 2) * S + s] += a.z;
+                sm[L::XT + (4 * k4 + 3) * S + s] += a.w;
             }
         }
         TILE_SYNC();
