@@ -13,10 +13,10 @@ Public surface mirrors the reference modules:
 from . import config, constants, train_losses
 from .fits_dict import FitsDict
 from .geometry import (batch_rodrigues, estimate_translation, perspective_projection, rot6d_to_rotmat,
-                       rotation_matrix_to_angle_axis, rotmat_to_rot6d)
+                       rotation_matrix_to_angle_axis, rotmat_to_rot6d, weak_perspective_projection)
 from .prior import MaxMixturePrior
 from .smpl import SMPL, ModelOutput
 from .smplify import SMPLify
 
 __all__ = ['SMPL', 'ModelOutput', 'SMPLify', 'MaxMixturePrior', 'FitsDict', 'batch_rodrigues', 'perspective_projection',
-           'rot6d_to_rotmat', 'rotmat_to_rot6d', 'rotation_matrix_to_angle_axis', 'estimate_translation', 'constants', 'config', 'train_losses']
+           'rot6d_to_rotmat', 'rotmat_to_rot6d', 'weak_perspective_projection', 'rotation_matrix_to_angle_axis', 'estimate_translation', 'constants', 'config', 'train_losses']

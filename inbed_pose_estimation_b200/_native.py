@@ -212,6 +212,10 @@ def _declare(lib):
     lib.smplb200_keypoint_3d_loss.argtypes = [ci] + [vp] * 7
     lib.smplb200_shape_loss.restype = ci
     lib.smplb200_shape_loss.argtypes = [ci] + [vp] * 7
+    lib.smplb200_weak_perspective_projection.restype = ci
+    lib.smplb200_weak_perspective_projection.argtypes = [ci, ci, vp, vp, cf, cf, vp, vp, vp]
+    lib.smplb200_weak_perspective_projection_backward.restype = ci
+    lib.smplb200_weak_perspective_projection_backward.argtypes = [ci, ci, vp, vp, cf, cf, vp, vp, vp, vp, vp]
     lib.smplb200_fit_tile_plan.restype = None
     lib.smplb200_fit_tile_plan.argtypes = [ci, ci] + [ctypes.POINTER(ci)] * 3
     lib.smplb200_smplify_fit_host.restype = ci
@@ -227,7 +231,8 @@ EXPORTED_SYMBOLS = (
     'smplb200_perspective_projection_backward', 'smplb200_smplify_fit_host', 'smplb200_launch_count', 'smplb200_probe_fp32_peak',
     'smplb200_rot6d_to_rotmat', 'smplb200_rotmat_to_axis_angle', 'smplb200_estimate_translation', 'smplb200_fits_get',
     'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
-    'smplb200_fit_tile_plan', 'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
+    'smplb200_fit_tile_plan', 'smplb200_weak_perspective_projection', 'smplb200_weak_perspective_projection_backward',
+    'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
 )
 
 

@@ -280,6 +280,58 @@ __global__ void __launch_bounds__(256) keep_better_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// train/trainer.py:187-199 (also :603-615, models/hmr.py:1708-1710, eval.py:245-247): weak-perspective camera [s, tx, ty]
+// -> translation [tx, ty, 2 f / (img_res s + 1e-9)], perspective projection of the joints with identity rotation and zero
+// camera centre, normalisation to [-1, 1] by img_res / 2.  One block per sample; same fp32 operation order as the eager ops.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) weak_persp_fwd_kernel(const float* __restrict__ joints, const float* __restrict__ cam, float focal,
+                                                            float img_res, float* __restrict__ cam_t, float* __restrict__ kp, int npts) {
+    const int b = blockIdx.x;
+    const float s = cam[3 * b], tx = cam[3 * b + 1], ty = cam[3 * b + 2];
+    // eager torch: two roundings in img_res * s + 1e-9 (no FMA), and scalar / tensor = tensor.reciprocal() * scalar
+    const float tz = __fmul_rn(__frcp_rn(__fadd_rn(__fmul_rn(img_res, s), 1e-9f)), 2.f * focal);
+    if (threadIdx.x == 0) { cam_t[3 * b] = tx; cam_t[3 * b + 1] = ty; cam_t[3 * b + 2] = tz; }
+    const float half = img_res / 2.f;
+    for (int n = threadIdx.x; n < npts; n += blockDim.x) {
+        const float* J = joints + ((size_t)b * npts + n) * 3;
+        const float x = J[0] + tx, y = J[1] + ty, z = J[2] + tz;
+        kp[((size_t)b * npts + n) * 2 + 0] = (focal * (x / z)) / half;
+        kp[((size_t)b * npts + n) * 2 + 1] = (focal * (y / z)) / half;
+    }
+}
+
+// gradients w.r.t. the joints and the weak-perspective camera; g_cam_t (may be null) is an extra gradient on the translation
+__global__ void __launch_bounds__(64) weak_persp_bwd_kernel(const float* __restrict__ joints, const float* __restrict__ cam, float focal,
+                                                            float img_res, const float* __restrict__ g_kp, const float* __restrict__ g_cam_t,
+                                                            float* __restrict__ g_joints, float* __restrict__ g_cam, int npts) {
+    __shared__ float red[3][64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float s = cam[3 * b], tx = cam[3 * b + 1], ty = cam[3 * b + 2];
+    const float den = __fadd_rn(__fmul_rn(img_res, s), 1e-9f);
+    const float tz = __fmul_rn(__frcp_rn(den), 2.f * focal);
+    const float c = focal / (img_res / 2.f);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int n = t; n < npts; n += blockDim.x) {
+        const float* J = joints + ((size_t)b * npts + n) * 3;
+        const float x = J[0] + tx, y = J[1] + ty, z = J[2] + tz;
+        const float gu = g_kp[((size_t)b * npts + n) * 2 + 0], gv = g_kp[((size_t)b * npts + n) * 2 + 1];
+        const float gx = gu * c / z, gy = gv * c / z, gz = -(gu * c * x + gv * c * y) / (z * z);
+        float* G = g_joints + ((size_t)b * npts + n) * 3;
+        G[0] = gx; G[1] = gy; G[2] = gz;
+        a0 += gx; a1 += gy; a2 += gz;
+    }
+    red[0][t] = a0; red[1][t] = a1; red[2][t] = a2;
+    __syncthreads();
+    if (t < 3) {
+        float a = 0.f;
+        for (int i = 0; i < 64; ++i) a += red[t][i];           // fixed order
+        if (g_cam_t) a += g_cam_t[3 * b + t];
+        if (t == 2) g_cam[3 * b + 0] = a * (-(2.f * focal) * img_res / (den * den));     // d tz / d s
+        else g_cam[3 * b + 1 + t] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 cudaError_t launch_rot6d_to_rotmat(const float* x, float* R, int n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     rot6d_to_rotmat_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, R, n);
@@ -319,6 +371,19 @@ cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, c
     if (batch <= 0) return cudaSuccess;
     keep_better_kernel<<<batch, 256, 0, st>>>(new_reproj, new_pose, new_betas, new_cam, new_joints, loss, pose, betas, cam, joints,
                                               update, batch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weak_persp_fwd(const float* joints, const float* cam, float focal, float img_res, float* cam_t, float* kp, int batch,
+                                  int npts, cudaStream_t st) {
+    if (batch <= 0) return cudaSuccess;
+    weak_persp_fwd_kernel<<<batch, 64, 0, st>>>(joints, cam, focal, img_res, cam_t, kp, npts);
+    return cudaGetLastError();
+}
+cudaError_t launch_weak_persp_bwd(const float* joints, const float* cam, float focal, float img_res, const float* g_kp,
+                                  const float* g_cam_t, float* g_joints, float* g_cam, int batch, int npts, cudaStream_t st) {
+    if (batch <= 0) return cudaSuccess;
+    weak_persp_bwd_kernel<<<batch, 64, 0, st>>>(joints, cam, focal, img_res, g_kp, g_cam_t, g_joints, g_cam, npts);
     return cudaGetLastError();
 }
 

@@ -339,6 +339,28 @@ extern "C" int smplb200_perspective_projection_backward(int batch, int num_point
     return 0;
 }
 
+extern "C" int smplb200_weak_perspective_projection(int batch, int num_points, const float* joints, const float* pred_camera,
+                                                    float focal_length, float img_res, float* camera_translation, float* keypoints_2d,
+                                                    void* stream) {
+    if (batch < 0 || num_points < 0 || (batch > 0 && (!joints || !pred_camera || !camera_translation || !keypoints_2d)))
+        return fail("weak_perspective_projection: bad arguments");
+    CUDA_OK(launch_weak_persp_fwd(joints, pred_camera, focal_length, img_res, camera_translation, keypoints_2d, batch, num_points,
+                                  static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+extern "C" int smplb200_weak_perspective_projection_backward(int batch, int num_points, const float* joints, const float* pred_camera,
+                                                             float focal_length, float img_res, const float* grad_keypoints_2d,
+                                                             const float* grad_camera_translation, float* grad_joints,
+                                                             float* grad_pred_camera, void* stream) {
+    if (batch < 0 || num_points < 0 || (batch > 0 && (!joints || !pred_camera || !grad_keypoints_2d || !grad_joints || !grad_pred_camera)))
+        return fail("weak_perspective_projection_backward: bad arguments");
+    CUDA_OK(launch_weak_persp_bwd(joints, pred_camera, focal_length, img_res, grad_keypoints_2d, grad_camera_translation, grad_joints,
+                                  grad_pred_camera, batch, num_points, static_cast<cudaStream_t>(stream)));
+    if (batch) ++g_launches;
+    return 0;
+}
+
 // ---- the steps either side of SMPLify -------------------------------------------------------------------
 extern "C" int smplb200_rot6d_to_rotmat(int n, const float* x6, float* rotmat, void* stream) {
     if (n < 0 || (n > 0 && (!x6 || !rotmat))) return fail("rot6d_to_rotmat: bad arguments");

@@ -35,6 +35,10 @@ cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, c
                                const float* new_joints, float* loss, float* pose, float* betas, float* cam, float* joints,
                                uint8_t* update, int batch, cudaStream_t st);
 
+cudaError_t launch_weak_persp_fwd(const float* joints, const float* cam, float focal, float img_res, float* cam_t, float* kp, int batch,
+                                  int npts, cudaStream_t st);
+cudaError_t launch_weak_persp_bwd(const float* joints, const float* cam, float focal, float img_res, const float* g_kp,
+                                  const float* g_cam_t, float* g_joints, float* g_cam, int batch, int npts, cudaStream_t st);
 
 // train_losses.cu: what the train step does with the SMPLify result
 size_t train_loss_workspace_doubles(int batch);

@@ -96,6 +96,47 @@ def perspective_projection(points, rotation, translation, focal_length, camera_c
 
 
 # ---- the steps either side of SMPLify -----------------------------------------------------------------
+class _WeakPerspective(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, joints, pred_camera, focal, img_res):
+        dev = joints.device
+        B, N = joints.shape[0], joints.shape[1]
+        j = joints.detach().contiguous().float()
+        c = pred_camera.detach().contiguous().float()
+        cam_t = torch.empty((B, 3), device=dev, dtype=torch.float32)
+        kp = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().smplb200_weak_perspective_projection(
+                B, N, _native.ptr(j), _native.ptr(c), float(focal), float(img_res), _native.ptr(cam_t), _native.ptr(kp), _stream(dev)))
+        ctx.save_for_backward(j, c)
+        ctx.consts = (float(focal), float(img_res))
+        ctx.set_materialize_grads(False)
+        return kp, cam_t
+
+    @staticmethod
+    def backward(ctx, g_kp, g_cam_t):
+        j, c = ctx.saved_tensors
+        B, N = j.shape[0], j.shape[1]
+        g_kp = torch.zeros((B, N, 2), device=j.device) if g_kp is None else g_kp.contiguous().float()
+        g_t = None if g_cam_t is None else g_cam_t.contiguous().float()
+        gj, gc = torch.empty_like(j), torch.empty_like(c)
+        with torch.cuda.device(j.device):
+            _native.check(_native.lib().smplb200_weak_perspective_projection_backward(
+                B, N, _native.ptr(j), _native.ptr(c), ctx.consts[0], ctx.consts[1], _native.ptr(g_kp), _native.ptr(g_t),
+                _native.ptr(gj), _native.ptr(gc), _stream(j.device)))
+        return gj, gc, None, None
+
+
+def weak_perspective_projection(joints, pred_camera, focal_length=5000., img_res=224):
+    """trainer.py:187-199 in one kernel: pred_camera [B,3] = (s, tx, ty) -> cam_t = (tx, ty, 2 f / (img_res s + 1e-9)); joints
+    [B,N,3] projected with it (identity rotation, zero centre) and normalised by img_res / 2.  Returns (keypoints_2d [B,N,2],
+    cam_t [B,3]); differentiable w.r.t. joints and pred_camera (cam_t.detach() is SMPLify's init_cam_t, trainer.py:713)."""
+    _require_cuda(joints, 'weak_perspective_projection')
+    if joints.dim() != 3 or joints.shape[2] != 3 or tuple(pred_camera.shape) != (joints.shape[0], 3):
+        raise ValueError('expected joints [B, N, 3] and pred_camera [B, 3]')
+    return _WeakPerspective.apply(joints, pred_camera, focal_length, img_res)
+
+
 def rot6d_to_rotmat(x):
     """6-D rotation representation -> rotation matrices (reference utils/geometry.py:47-61).
     x: (B, 6) or anything viewable as (-1, 3, 2); returns (N, 3, 3).  Forward only: in the reference this op sits

@@ -126,6 +126,17 @@ int smplb200_perspective_projection_backward(int batch, int num_points, const fl
                                              const float* grad_projected, float* grad_points, float* grad_rotation,
                                              float* grad_translation, void* stream);
 
+/* train/trainer.py:187-199 (and :603-615, models/hmr.py:1708-1710, eval.py:245-247): weak-perspective camera
+ * pred_camera [B][3] = (s, tx, ty) -> camera_translation [B][3] = (tx, ty, 2 f / (img_res s + 1e-9)) and the joints
+ * [B][N][3] projected with it (identity rotation, zero camera centre), divided by img_res / 2 -> keypoints_2d [B][N][2].
+ * The backward call takes d/d keypoints_2d (and optionally d/d camera_translation, may be NULL). */
+int smplb200_weak_perspective_projection(int batch, int num_points, const float* joints, const float* pred_camera, float focal_length,
+                                         float img_res, float* camera_translation, float* keypoints_2d, void* stream);
+int smplb200_weak_perspective_projection_backward(int batch, int num_points, const float* joints, const float* pred_camera,
+                                                  float focal_length, float img_res, const float* grad_keypoints_2d,
+                                                  const float* grad_camera_translation, float* grad_joints, float* grad_pred_camera,
+                                                  void* stream);
+
 /* ---- the steps either side of SMPLify in the reference's train step ------------------------------- */
 
 /* utils/geometry.py:47-61 rot6d_to_rotmat: [n][6] (viewed [n][3][2]) -> [n][3][3]. */

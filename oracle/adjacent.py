@@ -192,3 +192,12 @@ def finalize_fits(opt_pose, opt_betas, opt_cam_t, opt_joints, opt_vertices, opt_
     betas[has] = gt_betas[has]
     valid_fit = (opt_joint_loss < smplify_threshold) | has
     return pose, betas, cam, joints, verts, valid_fit
+
+
+def weak_perspective_projection(joints, pred_camera, focal_length=5000., img_res=224):
+    """trainer.py:187-199: (keypoints_2d normalised to [-1, 1], cam_t)."""
+    cam_t = torch.stack([pred_camera[:, 1], pred_camera[:, 2], 2 * focal_length / (img_res * pred_camera[:, 0] + 1e-9)], dim=-1)
+    p = joints + cam_t.unsqueeze(1)
+    proj = p / p[:, :, -1].unsqueeze(-1)
+    kp = focal_length * proj[:, :, :2]
+    return kp / (img_res / 2.), cam_t

@@ -164,3 +164,27 @@ def test_errors():
     with pytest.raises(ValueError):
         TL.smpl_losses(torch.zeros(2, 24, 3, 3).cuda(), torch.zeros(2, 10).cuda(), torch.zeros(2, 72).cuda(), torch.zeros(2, 10).cuda(),
                        torch.ones(3).cuda())
+
+
+def test_weak_perspective_projection(g):
+    """trainer.py:187-199 in one kernel: values bit-close to the reference's eager ops, gradients to 1e-5."""
+    from inbed_pose_estimation_b200 import geometry
+    cam, joints = C(g['wp_cam']).requires_grad_(True), C(g['wp_joints']).requires_grad_(True)
+    kp, cam_t = geometry.weak_perspective_projection(joints, cam, float(g['wp_focal']), float(g['wp_img_res']))
+    ((kp * C(g['wp_g_kp'])).sum() + (cam_t * C(g['wp_g_cam_t'])).sum()).backward()
+    np.testing.assert_allclose(kp.detach().cpu().numpy(), g['wp_kp'], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(cam_t.detach().cpu().numpy(), g['wp_cam_t'])
+    np.testing.assert_allclose(cam.grad.cpu().numpy(), g['wp_grad_cam'], rtol=1e-5, atol=1e-5 * float(np.abs(g['wp_grad_cam']).max()))
+    np.testing.assert_allclose(joints.grad.cpu().numpy(), g['wp_grad_joints'], rtol=1e-5, atol=1e-6)
+    # only the keypoints are used downstream; cam_t feeds SMPLify detached
+    cam2, joints2 = C(g['wp_cam']).requires_grad_(True), C(g['wp_joints']).requires_grad_(True)
+    kp2, t2 = geometry.weak_perspective_projection(joints2, cam2, float(g['wp_focal']), float(g['wp_img_res']))
+    kp2.sum().backward()
+    assert torch.isfinite(cam2.grad).all() and not t2.detach().requires_grad
+    big = torch.randn(4096, 49, 3, generator=torch.Generator().manual_seed(1))
+    bc = torch.cat([0.5 + torch.rand(4096, 1, generator=torch.Generator().manual_seed(2)), 0.1 * torch.randn(4096, 2, generator=torch.Generator().manual_seed(3))], dim=1)
+    k_ref, t_ref = adjacent.weak_perspective_projection(big, bc)
+    k_gpu, t_gpu = geometry.weak_perspective_projection(big.cuda(), bc.cuda())
+    np.testing.assert_allclose(k_gpu.cpu().numpy(), k_ref.numpy(), rtol=2e-6, atol=2e-6)
+    assert torch.equal(t_gpu.cpu(), t_ref)
+    assert geometry.weak_perspective_projection(torch.zeros(0, 49, 3).cuda(), torch.zeros(0, 3).cuda())[0].shape == (0, 49, 2)

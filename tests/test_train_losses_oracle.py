@@ -71,3 +71,13 @@ def test_finalize_fits(g):
         assert bool(torch.equal(verts[r], gv[r])) == bool(g['fin_out_vertices_from_gt'][r])
         assert bool(torch.equal(verts[r], ov[r])) == bool(g['fin_out_vertices_kept'][r])
     assert (betas[0] == 0).all() and torch.equal(betas[1], i('gt_betas')[1])       # extreme betas: zeroed / ground truth
+
+
+def test_weak_perspective_projection(g):
+    cam, joints = T(g['wp_cam']).clone().requires_grad_(True), T(g['wp_joints']).clone().requires_grad_(True)
+    kp, cam_t = adjacent.weak_perspective_projection(joints, cam, float(g['wp_focal']), float(g['wp_img_res']))
+    ((kp * T(g['wp_g_kp'])).sum() + (cam_t * T(g['wp_g_cam_t'])).sum()).backward()
+    np.testing.assert_allclose(kp.detach().numpy(), g['wp_kp'], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(cam_t.detach().numpy(), g['wp_cam_t'])
+    np.testing.assert_allclose(cam.grad.numpy(), g['wp_grad_cam'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(joints.grad.numpy(), g['wp_grad_joints'], rtol=1e-5, atol=1e-6)
