@@ -205,7 +205,7 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     if (batch < 0) return fail("negative batch");
     if (batch == 0) return 0;
     if (!loss_only && !m->has_prior) return fail("smplify_fit: the model was created without a GMM prior");
-    if (num_iters < 0 || num_iters > kMaxIters) return fail("num_iters must be in [0, %d]", kMaxIters);
+    if (num_iters < 0) return fail("num_iters must not be negative");
     if (!pose || !betas || !cam || !center || !kp || !reproj) return fail("smplify: NULL required buffer");
     if (ws_bytes < smplb200_fit_workspace_bytes(batch) || !ws) return fail("smplify: workspace too small");
     const Work wk = carve(ws, batch);

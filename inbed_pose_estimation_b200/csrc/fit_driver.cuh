@@ -43,6 +43,17 @@ struct FitParams {
     AdamConsts adam_c;
 };
 
+// Bias-correction scalars of Adam step `it` (0-based), computed in float64 like torch does on the host.  The first
+// kMaxIters steps of a stage are tabulated in shared memory once per tile; longer runs compute them on the fly.
+SB_HD AdamScalars adam_scalars(const FitParams& P, int it) {
+    const double bc1 = 1.0 - pow(P.beta1, (double)(it + 1));
+    const double bc2 = 1.0 - pow(P.beta2, (double)(it + 1));
+    AdamScalars sc;
+    sc.step_size = (float)(P.lr / bc1);
+    sc.bc2_sqrt = (float)sqrt(bc2);
+    return sc;
+}
+
 constexpr float kSigma2 = 100.f * 100.f;              // gmof sigma (losses.py:28)
 constexpr float kPosePriorW2 = (float)(4.78 * 4.78);  // pose_prior_weight ** 2
 constexpr float kAnglePriorW2 = (float)(15.2 * 15.2); // angle_prior_weight ** 2
@@ -211,7 +222,7 @@ SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int first, floa
             if (P.loss_trace && b < P.batch) P.loss_trace[(size_t)it * P.batch + b] = loss;
             float dth[3];
             rodrigues_bwd(th[0], th[1], th[2], dR, dth);
-            const AdamScalars sc = adam_tab[it];
+            const AdamScalars sc = (it < kMaxIters) ? adam_tab[it] : adam_scalars(P, it);
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 th[a] = adam_update(th[a], dth[a], mm[a], vv[a], P.adam_c, sc);
@@ -239,12 +250,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
     // per-iteration Adam scalars, computed in float64 like torch does on the host
     AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::ADAMTAB);
     const SmallConsts C = stage_small_consts<S>(M, sm);
-    FOR_ITEMS(t, P.num_iters) {
-        const double bc1 = 1.0 - pow(P.beta1, (double)(t + 1));
-        const double bc2 = 1.0 - pow(P.beta2, (double)(t + 1));
-        adam_tab[t].step_size = (float)(P.lr / bc1);
-        adam_tab[t].bc2_sqrt = (float)sqrt(bc2);
-    }
+    FOR_ITEMS(t, (P.num_iters < kMaxIters ? P.num_iters : kMaxIters)) adam_tab[t] = adam_scalars(P, t);
     // ---- load the tile ---------------------------------------------------------------------
     FOR_ITEMS(it, S * 72) {
         const int s = it / 72, k = it % 72, b = first + s;
@@ -319,7 +325,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
             PHASE_MARK(9);
             ph_gemm_and_chain_backward<S>(M, sm);
             PHASE_MARK(10);
-            const AdamScalars sc = adam_tab[it];
+            const AdamScalars sc = (it < kMaxIters) ? adam_tab[it] : adam_scalars(P, it);
             FOR_ITEMS(itj, kJoints * S) {
                 const int s = itj % S, j = itj / S;
                 float g[9], d[3];

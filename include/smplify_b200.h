@@ -31,7 +31,7 @@ extern "C" {
 #define SMPLB200_NUM_POSE_FEATURES 207
 #define SMPLB200_NUM_OUT_JOINTS 49
 #define SMPLB200_NUM_GAUSSIANS 8
-#define SMPLB200_MAX_ITERS 256
+#define SMPLB200_MAX_ITERS 256 /* Adam scalars of the first 256 steps per stage are tabulated on chip; longer fits work, a little slower */
 #define SMPLB200_VPOSED_PITCH 20736 /* floats per sample of the saved v_posed buffer (3*6890 padded; rows 16-byte aligned) */
 
 typedef struct smplb200_model smplb200_model;

@@ -130,3 +130,24 @@ def test_every_tile_mix_gives_the_same_fits(B, small):
         out_sub = fitter5(*_cuda(sub))
         for a, b in zip(out, out_sub):
             np.testing.assert_allclose(a[lo:hi].cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_more_iterations_than_the_on_chip_adam_table():
+    """num_iters is unbounded in the reference; here the Adam scalars of steps >= 256 are computed on the fly.  A 300 + 300
+    iteration fit must continue the 256-iteration trajectory (same first 256 losses per stage) and match the oracle at the end."""
+    from oracle import port
+    fit300 = synthetic.build_smplify('cuda', num_iters=300, seed=0)
+    fit256 = synthetic.build_smplify('cuda', num_iters=256, seed=0)
+    inp = synthetic.make_fit_inputs(6, seed=77)
+    out = fit300(*_cuda(inp), return_loss_trace=True)
+    tr300 = fit300.last_loss_trace.cpu().numpy()
+    fit256(*_cuda(inp), return_loss_trace=True)
+    tr256 = fit256.last_loss_trace.cpu().numpy()
+    assert np.array_equal(tr300[:256], tr256[:256])                        # stage 1: identical prefix
+    assert np.all(np.isfinite(tr300))
+    oracle = port.build_oracle(seed=0, num_iters=300)
+    trace = []
+    ref = oracle(*[torch.from_numpy(inp[k].copy()) for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')], trace=trace)
+    tr_o = torch.stack(trace).double().sum(1).numpy()
+    np.testing.assert_allclose(tr300.astype(np.float64).sum(1), tr_o, rtol=1e-5)
+    np.testing.assert_allclose(out[2].cpu().numpy(), ref[2].numpy(), atol=1e-4)
