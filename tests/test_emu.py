@@ -118,3 +118,21 @@ def test_fit_matches_reference_run(emu, variant):
     assert np.all(out['keypoints'][:, C.SMPLIFY_IGNORED_JOINTS, 2] == 0)
     keep = [j for j in range(49) if j not in C.SMPLIFY_IGNORED_JOINTS]
     assert np.array_equal(out['keypoints'][:, keep], g['keypoints'][:, keep])
+
+
+def test_fit_beyond_the_on_chip_adam_table(emu):
+    """Steps >= 256 of a stage take their Adam bias corrections from adam_scalars() on the fly (the table in shared memory
+    holds 256): a 270 + 270 iteration fit must track the oracle to the end, and its first 256 camera-stage losses must be
+    those of a 256-iteration fit (same table)."""
+    from oracle import port
+    inp = synthetic.make_fit_inputs(2, seed=31)
+    out = emu.fit(inp, num_iters=270)
+    short = emu.fit(inp, num_iters=256)
+    assert np.array_equal(out['trace'][:256], short['trace'][:256])
+    oracle = port.build_oracle(seed=0, num_iters=270)
+    trace = []
+    ref = oracle(*[torch.from_numpy(inp[k].copy()) for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')], trace=trace)
+    tr_o = torch.stack(trace).double().sum(1).numpy()
+    np.testing.assert_allclose(out['trace'].astype(np.float64).sum(1), tr_o, rtol=1e-5)
+    np.testing.assert_allclose(out['pose'], ref[2].numpy(), atol=1e-4)
+    np.testing.assert_allclose(out['cam_t'], ref[4].numpy(), atol=1e-4)
