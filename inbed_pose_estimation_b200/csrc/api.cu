@@ -28,6 +28,8 @@ struct smplb200_model {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device -> host copies of the fit results overlap the vertex kernels
+    cudaEvent_t fit_done = nullptr;
 };
 
 static thread_local std::string g_error;
@@ -141,6 +143,8 @@ extern "C" void smplb200_model_destroy(smplb200_model* m) {
     for (void* p : m->allocations) cudaFree(p);
     if (m->scratch) cudaFree(m->scratch);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    if (m->fit_done) cudaEventDestroy(m->fit_done);
     delete m;
 }
 
@@ -200,7 +204,7 @@ static AdamConsts adam_consts(double beta1, double beta2) {
 static int run_fit(const smplb200_model* m, int batch, int num_iters, float step_size, float focal, int loss_only,
                    const float* pose, const float* betas, const float* cam, const float* center, float* kp,
                    float* vertices, float* joints, float* opose, float* obetas, float* ocam, float* reproj, float* trace,
-                   void* ws, size_t ws_bytes, cudaStream_t st) {
+                   void* ws, size_t ws_bytes, cudaStream_t st, cudaEvent_t after_fit = nullptr) {
     if (!m) return fail("NULL model");
     if (batch < 0) return fail("negative batch");
     if (batch == 0) return 0;
@@ -223,6 +227,7 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     P.adam_c = adam_consts(P.beta1, P.beta2);
     CUDA_OK(launch_fit(m->view, P, st));
     ++g_launches;
+    if (after_fit) CUDA_OK(cudaEventRecord(after_fit, st));          // parameters / joints / losses are final here
     if (vertices && run_vertices(m, wk, wk.big0, vertices, batch, st)) return 1;
     return 0;
 }
@@ -479,6 +484,8 @@ extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, in
     std::lock_guard<std::mutex> lock(m->mu);
     CUDA_OK(cudaSetDevice(m->device));
     if (!m->host_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
+    if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (!m->fit_done) CUDA_OK(cudaEventCreateWithFlags(&m->fit_done, cudaEventDisableTiming));
     const size_t B = (size_t)batch;
     const size_t n_in = B * (72 + 10 + 3 + 2 + 147), n_out = B * (147 + 72 + 10 + 3 + 49);
     const size_t need = align256(n_in * 4) + align256(n_out * 4) + align256(B * kCols * 4) +
@@ -508,15 +515,19 @@ extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, in
     CUDA_OK(cudaMemcpyAsync(d_cen, camera_center, B * 2 * 4, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaMemcpyAsync(d_kp, keypoints_2d, B * 147 * 4, cudaMemcpyHostToDevice, st));
     if (run_fit(m, batch, num_iters, step_size, focal_length, 0, d_pose, d_betas, d_cam, d_cen, d_kp, d_verts, o_joints, o_pose,
-                o_betas, o_cam, o_reproj, nullptr, ws, smplb200_fit_workspace_bytes(batch), st))
+                o_betas, o_cam, o_reproj, nullptr, ws, smplb200_fit_workspace_bytes(batch), st, m->fit_done))
         return 1;
-    CUDA_OK(cudaMemcpyAsync(joints, o_joints, B * 147 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(pose, o_pose, B * 72 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(betas, o_betas, B * 10 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(camera_translation, o_cam, B * 3 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(reprojection_loss, o_reproj, B * 49 * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(keypoints_2d, d_kp, B * 147 * 4, cudaMemcpyDeviceToHost, st));   // in-place confidence zeroing
+    // the fit results leave on a second stream as soon as the fit kernel is done, while `st` runs the vertex kernels
+    cudaStream_t cs = m->copy_stream;
+    CUDA_OK(cudaStreamWaitEvent(cs, m->fit_done, 0));
+    CUDA_OK(cudaMemcpyAsync(joints, o_joints, B * 147 * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(pose, o_pose, B * 72 * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(betas, o_betas, B * 10 * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(camera_translation, o_cam, B * 3 * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(reprojection_loss, o_reproj, B * 49 * 4, cudaMemcpyDeviceToHost, cs));
+    CUDA_OK(cudaMemcpyAsync(keypoints_2d, d_kp, B * 147 * 4, cudaMemcpyDeviceToHost, cs));   // in-place confidence zeroing
     if (vertices) CUDA_OK(cudaMemcpyAsync(vertices, d_verts, B * kCols * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(cs));
     CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

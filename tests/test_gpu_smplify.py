@@ -151,3 +151,28 @@ def test_more_iterations_than_the_on_chip_adam_table():
     tr_o = torch.stack(trace).double().sum(1).numpy()
     np.testing.assert_allclose(tr300.astype(np.float64).sum(1), tr_o, rtol=1e-5)
     np.testing.assert_allclose(out[2].cpu().numpy(), ref[2].numpy(), atol=1e-4)
+
+
+def test_host_buffer_entry_point_equals_device_path(fitter):
+    """smplb200_smplify_fit_host (what bench.py times as e2e: H2D, fit, vertex kernels, D2H on two streams) returns the
+    same bits as the device-pointer path, zeroes the ignored confidences in the caller's host buffer and fills vertices."""
+    import ctypes
+    from inbed_pose_estimation_b200 import _native
+    B = 70
+    inp = synthetic.make_fit_inputs(B, seed=123)
+    dev = fitter(*_cuda(inp))
+    lib = _native.lib()
+    h = {k: np.ascontiguousarray(inp[k], dtype=np.float32).copy() for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')}
+    out = {'verts': np.empty((B, 6890, 3), np.float32), 'joints': np.empty((B, 49, 3), np.float32), 'pose': np.empty((B, 72), np.float32),
+           'betas': np.empty((B, 10), np.float32), 'cam': np.empty((B, 3), np.float32), 'reproj': np.empty((B, 49), np.float32)}
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    handle = fitter.smpl.native(torch.device('cuda', torch.cuda.current_device())).handle
+    for with_verts in (True, False):
+        kp = h['keypoints'].copy()
+        _native.check(lib.smplb200_smplify_fit_host(handle, B, 100, 1e-2, 5000., p(h['pose']), p(h['betas']), p(h['cam_t']), p(h['center']),
+                                                    p(kp), p(out['verts']) if with_verts else None, p(out['joints']), p(out['pose']),
+                                                    p(out['betas']), p(out['cam']), p(out['reproj'])))
+        for got, ref in ((out['joints'], dev[1]), (out['pose'], dev[2]), (out['betas'], dev[3]), (out['cam'], dev[4]), (out['reproj'], dev[5])):
+            assert np.array_equal(got, ref.cpu().numpy())
+        assert np.all(kp[:, C.SMPLIFY_IGNORED_JOINTS, 2] == 0)
+    assert np.array_equal(out['verts'], dev[0].cpu().numpy())
