@@ -73,3 +73,17 @@ def test_fit_tile_plan_covers_every_batch_in_the_fewest_waves():
     assert _native.fit_tile_plan(32, sms) == (0, 4, 8)
     assert _native.fit_tile_plan(4736, sms) == (296, 0, 0)
     assert _native.fit_tile_plan(0, sms) == (0, 0, 0)
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: no file of the package (Python or CUDA/C++) may import, include or open it."""
+    pkg = os.path.join(ROOT, 'inbed_pose_estimation_b200')
+    for folder, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith(('.py', '.cu', '.cuh', '.h', '.cpp')):
+                continue
+            text = open(os.path.join(folder, f), errors='replace').read()
+            assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+            assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), f
+            for literal in re.findall(r'"[^"\n]*"|\'[^\'\n]*\'', text):           # paths only appear in comments
+                assert 'oracle' not in literal and '/root/reference' not in literal, (f, literal)
