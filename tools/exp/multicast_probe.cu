@@ -8,7 +8,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-constexpr int kStageBytes = 32 * 1024, kStages = 4, kThreads = 160;   // warp 0 producer, warps 1-4 consumers
+#ifndef STAGES
+#define STAGES 4
+#endif
+constexpr int kStageBytes = 32 * 1024, kStages = STAGES, kThreads = 160;   // warp 0 producer, warps 1-4 consumers
 constexpr long long kTimeoutClk = 4000000000LL;                       // ~2 s: trap instead of hanging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,9 +100,9 @@ __global__ void __launch_bounds__(kThreads, 1) stream_kernel(const char* src, in
 }
 
 template <int CS, bool READ>
-void run(const char* d_src, int chunks, int iters, long long* d_cyc, float* d_sink) {
+void run(const char* d_src, int chunks, int iters, long long* d_cyc, float* d_sink, int grid = 148) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(148);
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kStages * kStageBytes;
     cudaLaunchAttribute at[1];
@@ -123,10 +126,10 @@ void run(const char* d_src, int chunks, int iters, long long* d_cyc, float* d_si
     long long h[148];
     cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
     long long mx = 0;
-    for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
     const double bytes = (double)chunks * iters * kStageBytes;
-    printf("cluster %d read %d: %.3f ms, %.0f cycles per pass of %.2f MB, %.1f B/clk into each SM, %.2f TB/s out of L2 chip-wide\n",
-           CS, (int)READ, ms, (double)mx / iters, chunks * kStageBytes / 1e6, bytes / mx, bytes * 148 / CS / (ms * 1e-3) / 1e12);
+    printf("grid %d stages %d cluster %d read %d: %.3f ms, %.0f cycles per pass of %.2f MB, %.1f B/clk into each SM, %.2f TB/s out of L2 chip-wide\n",
+           grid, kStages, CS, (int)READ, ms, (double)mx / iters, chunks * kStageBytes / 1e6, bytes / mx, bytes * grid / CS / (ms * 1e-3) / 1e12);
 }
 
 int main() {
@@ -140,6 +143,8 @@ int main() {
     run<2, false>(d_src, chunks, iters, d_cyc, d_sink);
     run<4, false>(d_src, chunks, iters, d_cyc, d_sink);
     run<1, true>(d_src, chunks, iters, d_cyc, d_sink);
+    for (int g : {8, 32, 64, 104}) run<1, false>(d_src, chunks, iters, d_cyc, d_sink, g);
+    for (int g : {8, 64}) run<2, false>(d_src, chunks, iters, d_cyc, d_sink, g);
     run<2, true>(d_src, chunks, iters, d_cyc, d_sink);
     run<4, true>(d_src, chunks, iters, d_cyc, d_sink);
     return 0;
