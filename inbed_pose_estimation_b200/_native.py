@@ -158,7 +158,7 @@ def make_desc(arrays, prior=None):
 
 
 def _declare(lib):
-    vp, sz, ci, cf = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float
+    vp, sz, ci, cf, cd, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_int64
     lib.smplb200_version.restype = ci
     lib.smplb200_last_error.restype = ctypes.c_char_p
     lib.smplb200_launch_count.restype = ctypes.c_longlong
@@ -171,9 +171,11 @@ def _declare(lib):
         getattr(lib, name).restype = sz
         getattr(lib, name).argtypes = [ci]
     lib.smplb200_smplify_fit.restype = ci
-    lib.smplb200_smplify_fit.argtypes = [vp, ci, ci, cf, cf] + [vp] * 12 + [vp, sz, vp]
+    lib.smplb200_smplify_fit.argtypes = [vp, ci, ci, cd, cf] + [vp] * 12 + [vp, sz, vp]
     lib.smplb200_smplify_fitting_loss.restype = ci
     lib.smplb200_smplify_fitting_loss.argtypes = [vp, ci, cf] + [vp] * 6 + [vp, sz, vp]
+    lib.smplb200_prior_terms.restype = ci
+    lib.smplb200_prior_terms.argtypes = [vp, ci] + [vp] * 8
     lib.smplb200_smpl_forward.restype = ci
     lib.smplb200_smpl_forward.argtypes = [vp, ci, ci] + [vp] * 5 + [vp, sz, vp]
     lib.smplb200_smpl_backward.restype = ci
@@ -183,9 +185,9 @@ def _declare(lib):
     lib.smplb200_batch_rodrigues_backward.restype = ci
     lib.smplb200_batch_rodrigues_backward.argtypes = [ci, vp, vp, vp, vp]
     lib.smplb200_perspective_projection.restype = ci
-    lib.smplb200_perspective_projection.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp]
+    lib.smplb200_perspective_projection.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, ci, vp, vp]
     lib.smplb200_perspective_projection_backward.restype = ci
-    lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]
+    lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.smplb200_probe_fp32_peak.restype = ci
     lib.smplb200_probe_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     lib.smplb200_rot6d_to_rotmat.restype = ci
@@ -195,9 +197,9 @@ def _declare(lib):
     lib.smplb200_estimate_translation.restype = ci
     lib.smplb200_estimate_translation.argtypes = [ci, vp, vp, cf, cf, vp, vp]
     lib.smplb200_fits_get.restype = ci
-    lib.smplb200_fits_get.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.smplb200_fits_get.argtypes = [ci, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.smplb200_fits_set.restype = ci
-    lib.smplb200_fits_set.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.smplb200_fits_set.argtypes = [ci, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.smplb200_keep_better.restype = ci
     lib.smplb200_keep_better.argtypes = [ci] + [vp] * 12
     lib.smplb200_finalize_fits.restype = ci
@@ -219,7 +221,7 @@ def _declare(lib):
     lib.smplb200_fit_tile_plan.restype = None
     lib.smplb200_fit_tile_plan.argtypes = [ci, ci] + [ctypes.POINTER(ci)] * 3
     lib.smplb200_smplify_fit_host.restype = ci
-    lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cf, cf] + [vp] * 11
+    lib.smplb200_smplify_fit_host.argtypes = [vp, ci, ci, cd, cf] + [vp] * 11
     return lib
 
 
@@ -233,6 +235,7 @@ EXPORTED_SYMBOLS = (
     'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
     'smplb200_fit_tile_plan', 'smplb200_weak_perspective_projection', 'smplb200_weak_perspective_projection_backward',
     'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
+    'smplb200_prior_terms',
 )
 
 

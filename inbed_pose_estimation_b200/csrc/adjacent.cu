@@ -205,13 +205,23 @@ __device__ __forceinline__ void rotate_global(float* go, float rot_deg) {
 struct FlipPerm { uint8_t p[72]; };      // constants.SMPL_POSE_FLIP_PERM
 
 // __getitem__: rows of the [N][82] store -> rotate -> flip
-__global__ void __launch_bounds__(96) fits_get_kernel(const float* __restrict__ store, const long long* __restrict__ index,
+// Rows whose index falls outside [0, store_rows) are not touched in the store: the get returns NaNs for them, the set skips
+// them, and both raise bit 0 of *status (device memory, nullable) - the bounds check needs no host round trip.
+__global__ void __launch_bounds__(96) fits_get_kernel(const float* __restrict__ store, long long store_rows,
+                                                      const long long* __restrict__ index,
                                                       const float* __restrict__ rot, const uint8_t* __restrict__ flipped,
                                                       const __grid_constant__ FlipPerm perm, float* __restrict__ pose,
-                                                      float* __restrict__ betas, int batch) {
+                                                      float* __restrict__ betas, int* __restrict__ status, int batch) {
     __shared__ float row[82];
     const int b = blockIdx.x, t = threadIdx.x;
-    if (t < 82) row[t] = store[(size_t)index[b] * 82 + t];
+    const long long idx = index[b];
+    if (idx < 0 || idx >= store_rows) {                          // block-uniform
+        if (t == 0 && status) atomicOr(status, 1);
+        if (t < 72) pose[(size_t)b * 72 + t] = __int_as_float(0x7fc00000);
+        else if (t < 82) betas[(size_t)b * 10 + t - 72] = __int_as_float(0x7fc00000);
+        return;
+    }
+    if (t < 82) row[t] = store[(size_t)idx * 82 + t];
     __syncthreads();
     if (t == 0) rotate_global(row, rot[b]);
     __syncthreads();
@@ -228,12 +238,19 @@ __global__ void __launch_bounds__(96) fits_get_kernel(const float* __restrict__ 
 }
 
 // __setitem__: flip -> rotate by -rot -> masked scatter into the store
-__global__ void __launch_bounds__(96) fits_set_kernel(float* __restrict__ store, const long long* __restrict__ index,
+__global__ void __launch_bounds__(96) fits_set_kernel(float* __restrict__ store, long long store_rows,
+                                                      const long long* __restrict__ index,
                                                       const float* __restrict__ rot, const uint8_t* __restrict__ flipped,
                                                       const uint8_t* __restrict__ update, const __grid_constant__ FlipPerm perm,
-                                                      const float* __restrict__ pose, const float* __restrict__ betas, int batch) {
+                                                      const float* __restrict__ pose, const float* __restrict__ betas,
+                                                      int* __restrict__ status, int batch) {
     __shared__ float row[82];
     const int b = blockIdx.x, t = threadIdx.x;
+    const long long idx = index[b];
+    if (idx < 0 || idx >= store_rows) {                          // reported whether or not the row was to be updated
+        if (t == 0 && status) atomicOr(status, 1);
+        return;
+    }
     if (!update[b]) return;
     if (t < 72) {
         float v = pose[(size_t)b * 72 + t];
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(96) fits_set_kernel(float* __restrict__ store,
     __syncthreads();
     if (t == 0) rotate_global(row, -rot[b]);
     __syncthreads();
-    if (t < 82) store[(size_t)index[b] * 82 + t] = row[t];
+    if (t < 82) store[(size_t)idx * 82 + t] = row[t];
 }
 
 // trainer.py:716-727: update = new_loss < old_loss (new_loss = mean over the 49 joints of the new reprojection loss);
@@ -353,16 +370,17 @@ static FlipPerm make_perm(const int* perm72) {
     for (int i = 0; i < 72; ++i) p.p[i] = (uint8_t)perm72[i];
     return p;
 }
-cudaError_t launch_fits_get(const float* store, const long long* index, const float* rot, const uint8_t* flipped, const int* perm72,
-                            float* pose, float* betas, int batch, cudaStream_t st) {
+cudaError_t launch_fits_get(const float* store, long long store_rows, const long long* index, const float* rot, const uint8_t* flipped,
+                            const int* perm72, float* pose, float* betas, int* status, int batch, cudaStream_t st) {
     if (batch <= 0) return cudaSuccess;
-    fits_get_kernel<<<batch, 96, 0, st>>>(store, index, rot, flipped, make_perm(perm72), pose, betas, batch);
+    fits_get_kernel<<<batch, 96, 0, st>>>(store, store_rows, index, rot, flipped, make_perm(perm72), pose, betas, status, batch);
     return cudaGetLastError();
 }
-cudaError_t launch_fits_set(float* store, const long long* index, const float* rot, const uint8_t* flipped, const uint8_t* update,
-                            const int* perm72, const float* pose, const float* betas, int batch, cudaStream_t st) {
+cudaError_t launch_fits_set(float* store, long long store_rows, const long long* index, const float* rot, const uint8_t* flipped,
+                            const uint8_t* update, const int* perm72, const float* pose, const float* betas, int* status, int batch,
+                            cudaStream_t st) {
     if (batch <= 0) return cudaSuccess;
-    fits_set_kernel<<<batch, 96, 0, st>>>(store, index, rot, flipped, update, make_perm(perm72), pose, betas, batch);
+    fits_set_kernel<<<batch, 96, 0, st>>>(store, store_rows, index, rot, flipped, update, make_perm(perm72), pose, betas, status, batch);
     return cudaGetLastError();
 }
 cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, const float* new_betas, const float* new_cam,

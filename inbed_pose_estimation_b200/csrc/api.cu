@@ -50,7 +50,27 @@ static int fail(const char* fmt, ...) {
         if (_e != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(_e));   \
     } while (0)
 
-extern "C" int smplb200_version(void) { return 100; }
+// Makes `device` current for the scope and restores the caller's current device on every exit path: the entry points
+// that own a device (create / destroy / the host-buffer fit) must not leave a different device current behind them.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            switched = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+extern "C" int smplb200_version(void) { return 200; }
 extern "C" void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_small) {
     int a = 0, b = 0, c = 0;
     if (batch > 0 && sms > 0) plan_fit_tiles(batch, sms, &a, &b, &c);
@@ -98,7 +118,8 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
     HostModel H;
     const std::string err = build_host_model(*desc, H);
     if (!err.empty()) return fail("smplb200_model_create: %s", err.c_str());
-    CUDA_OK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_OK(guard.err);
     smplb200_model* m = new smplb200_model();
     m->device = device;
     m->view = H.view;
@@ -139,7 +160,7 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
 
 extern "C" void smplb200_model_destroy(smplb200_model* m) {
     if (!m) return;
-    cudaSetDevice(m->device);
+    DeviceGuard guard(m->device);
     for (void* p : m->allocations) cudaFree(p);
     if (m->scratch) cudaFree(m->scratch);
     if (m->host_stream) cudaStreamDestroy(m->host_stream);
@@ -201,7 +222,7 @@ static AdamConsts adam_consts(double beta1, double beta2) {
     return c;
 }
 
-static int run_fit(const smplb200_model* m, int batch, int num_iters, float step_size, float focal, int loss_only,
+static int run_fit(const smplb200_model* m, int batch, int num_iters, double step_size, float focal, int loss_only,
                    const float* pose, const float* betas, const float* cam, const float* center, float* kp,
                    float* vertices, float* joints, float* opose, float* obetas, float* ocam, float* reproj, float* trace,
                    void* ws, size_t ws_bytes, cudaStream_t st, cudaEvent_t after_fit = nullptr) {
@@ -223,7 +244,7 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     P.out_joints = joints; P.out_pose = opose; P.out_betas = obetas; P.out_cam = ocam; P.out_reproj = reproj;
     if (vertices) P.tc = wk.tc;
     P.loss_trace = trace;
-    P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
+    P.lr = step_size; P.beta1 = 0.9; P.beta2 = 0.999;        // lr stays a double: torch divides the Python float by bc1
     P.adam_c = adam_consts(P.beta1, P.beta2);
     CUDA_OK(launch_fit(m->view, P, st));
     ++g_launches;
@@ -232,7 +253,7 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, float step
     return 0;
 }
 
-extern "C" int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+extern "C" int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, double step_size, float focal_length,
                                     const float* init_pose, const float* init_betas, const float* init_cam_t,
                                     const float* camera_center, float* keypoints_2d, float* vertices, float* joints,
                                     float* pose, float* betas, float* camera_translation, float* reprojection_loss,
@@ -247,9 +268,25 @@ extern "C" int smplb200_smplify_fitting_loss(const smplb200_model* model, int ba
                                              const float* betas, const float* cam_t, const float* camera_center,
                                              float* keypoints_2d, float* reprojection_loss, void* workspace,
                                              size_t workspace_bytes, void* stream) {
-    return run_fit(model, batch, 0, 0.f, focal_length, 1, pose, betas, cam_t, camera_center, keypoints_2d, nullptr, nullptr,
+    return run_fit(model, batch, 0, 0.0, focal_length, 1, pose, betas, cam_t, camera_center, keypoints_2d, nullptr, nullptr,
                    nullptr, nullptr, nullptr, reprojection_loss, nullptr, workspace, workspace_bytes,
                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int smplb200_prior_terms(const smplb200_model* m, int batch, const float* pose, const float* betas, float* terms,
+                                    float* components, int32_t* argmin, float* grad_body_pose, float* grad_betas, void* stream) {
+    if (!m) return fail("NULL model");
+    if (!m->has_prior) return fail("prior_terms: the model was created without a GMM prior");
+    if (batch < 0) return fail("negative batch");
+    if (batch == 0) return 0;
+    if (!pose || !betas || !terms) return fail("prior_terms: NULL required buffer");
+    PriorParams P;
+    memset(&P, 0, sizeof(P));
+    P.batch = batch; P.pose = pose; P.betas = betas; P.terms = terms; P.components = components;
+    P.argmin = reinterpret_cast<int*>(argmin); P.grad_body_pose = grad_body_pose; P.grad_betas = grad_betas;
+    CUDA_OK(launch_prior_terms(m->view, P, static_cast<cudaStream_t>(stream)));
+    ++g_launches;
+    return 0;
 }
 
 extern "C" int smplb200_smpl_forward(const smplb200_model* m, int batch, int rotmat_mode, const float* pose, const float* betas,
@@ -320,25 +357,25 @@ extern "C" int smplb200_batch_rodrigues_backward(int n, const float* theta, cons
 
 extern "C" int smplb200_perspective_projection(int batch, int num_points, const float* points, const float* rotation,
                                                const float* translation, const float* focal_length, int focal_per_batch,
-                                               const float* camera_center, float* projected, void* stream) {
+                                               const float* camera_center, int out_3d, float* projected, void* stream) {
     if (batch < 0 || num_points < 0) return fail("perspective_projection: negative size");
     if ((size_t)batch * num_points == 0) return 0;
     if (!points || !rotation || !translation || !focal_length || !camera_center || !projected)
         return fail("perspective_projection: NULL buffer");
-    CUDA_OK(launch_projection_fwd(points, rotation, translation, focal_length, focal_per_batch, camera_center, projected, batch,
-                                  num_points, static_cast<cudaStream_t>(stream)));
+    CUDA_OK(launch_projection_fwd(points, rotation, translation, focal_length, focal_per_batch, camera_center, projected, out_3d != 0,
+                                  batch, num_points, static_cast<cudaStream_t>(stream)));
     ++g_launches;
     return 0;
 }
 extern "C" int smplb200_perspective_projection_backward(int batch, int num_points, const float* points, const float* rotation,
                                                         const float* translation, const float* focal_length, int focal_per_batch,
-                                                        const float* grad_projected, float* grad_points, float* grad_rotation,
-                                                        float* grad_translation, void* stream) {
+                                                        int out_3d, const float* grad_projected, float* grad_points,
+                                                        float* grad_rotation, float* grad_translation, void* stream) {
     if (batch < 0 || num_points < 0) return fail("perspective_projection_backward: negative size");
     if (batch == 0) return 0;
     if (!points || !rotation || !translation || !focal_length || !grad_projected || !grad_points || !grad_rotation || !grad_translation)
         return fail("perspective_projection_backward: NULL buffer");
-    CUDA_OK(launch_projection_bwd(points, rotation, translation, focal_length, focal_per_batch, grad_projected, grad_points,
+    CUDA_OK(launch_projection_bwd(points, rotation, translation, focal_length, focal_per_batch, grad_projected, out_3d != 0, grad_points,
                                   grad_rotation, grad_translation, batch, num_points, static_cast<cudaStream_t>(stream)));
     ++g_launches;
     return 0;
@@ -386,27 +423,32 @@ extern "C" int smplb200_estimate_translation(int batch, const float* joints3d, c
     if (batch) ++g_launches;
     return 0;
 }
-extern "C" int smplb200_fits_get(int batch, const float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
-                                 const int32_t* pose_flip_perm, float* pose, float* betas, void* stream) {
-    if (batch < 0 || (batch > 0 && (!store || !index || !rot_deg || !flipped || !pose_flip_perm || !pose || !betas)))
+extern "C" int smplb200_fits_get(int batch, const float* store, int64_t store_rows, const int64_t* index, const float* rot_deg,
+                                 const uint8_t* flipped, const int32_t* pose_flip_perm, float* pose, float* betas, int32_t* status,
+                                 void* stream) {
+    if (batch < 0) return fail("fits_get: negative batch");
+    if (batch == 0) return 0;
+    if (!store || store_rows < 0 || !index || !rot_deg || !flipped || !pose_flip_perm || !pose || !betas)
         return fail("fits_get: bad arguments");
     for (int i = 0; i < 72; ++i)
         if (pose_flip_perm[i] < 0 || pose_flip_perm[i] >= 72) return fail("fits_get: pose_flip_perm[%d] out of range", i);
-    CUDA_OK(launch_fits_get(store, reinterpret_cast<const long long*>(index), rot_deg, flipped, pose_flip_perm, pose, betas, batch,
-                            static_cast<cudaStream_t>(stream)));
-    if (batch) ++g_launches;
+    CUDA_OK(launch_fits_get(store, (long long)store_rows, reinterpret_cast<const long long*>(index), rot_deg, flipped, pose_flip_perm,
+                            pose, betas, status, batch, static_cast<cudaStream_t>(stream)));
+    ++g_launches;
     return 0;
 }
-extern "C" int smplb200_fits_set(int batch, float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
-                                 const uint8_t* update, const int32_t* pose_flip_perm, const float* pose, const float* betas,
-                                 void* stream) {
-    if (batch < 0 || (batch > 0 && (!store || !index || !rot_deg || !flipped || !update || !pose_flip_perm || !pose || !betas)))
+extern "C" int smplb200_fits_set(int batch, float* store, int64_t store_rows, const int64_t* index, const float* rot_deg,
+                                 const uint8_t* flipped, const uint8_t* update, const int32_t* pose_flip_perm, const float* pose,
+                                 const float* betas, int32_t* status, void* stream) {
+    if (batch < 0) return fail("fits_set: negative batch");
+    if (batch == 0) return 0;
+    if (!store || store_rows < 0 || !index || !rot_deg || !flipped || !update || !pose_flip_perm || !pose || !betas)
         return fail("fits_set: bad arguments");
     for (int i = 0; i < 72; ++i)
         if (pose_flip_perm[i] < 0 || pose_flip_perm[i] >= 72) return fail("fits_set: pose_flip_perm[%d] out of range", i);
-    CUDA_OK(launch_fits_set(store, reinterpret_cast<const long long*>(index), rot_deg, flipped, update, pose_flip_perm, pose, betas,
-                            batch, static_cast<cudaStream_t>(stream)));
-    if (batch) ++g_launches;
+    CUDA_OK(launch_fits_set(store, (long long)store_rows, reinterpret_cast<const long long*>(index), rot_deg, flipped, update,
+                            pose_flip_perm, pose, betas, status, batch, static_cast<cudaStream_t>(stream)));
+    ++g_launches;
     return 0;
 }
 extern "C" int smplb200_keep_better(int batch, const float* new_reprojection_loss, const float* new_pose, const float* new_betas,
@@ -474,15 +516,21 @@ extern "C" int smplb200_shape_loss(int batch, const float* pred_vertices, const 
 }
 
 // Host-buffer wrapper: H2D of the five inputs, fit, D2H of the results, synchronise.
-extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, int num_iters, float step_size, float focal_length,
+extern "C" int smplb200_smplify_fit_host(const smplb200_model* cm, int batch, int num_iters, double step_size, float focal_length,
                                          const float* init_pose, const float* init_betas, const float* init_cam_t,
                                          const float* camera_center, float* keypoints_2d, float* vertices, float* joints,
                                          float* pose, float* betas, float* camera_translation, float* reprojection_loss) {
     if (!cm) return fail("NULL model");
     if (batch <= 0) return batch == 0 ? 0 : fail("negative batch");
+    if (!init_pose || !init_betas || !init_cam_t || !camera_center || !keypoints_2d)
+        return fail("smplify_fit_host: NULL input buffer");
+    if (!joints || !pose || !betas || !camera_translation || !reprojection_loss) return fail("smplify_fit_host: NULL output buffer");
+    if (!cm->has_prior) return fail("smplify_fit_host: the model was created without a GMM prior");
+    if (num_iters < 0) return fail("num_iters must not be negative");
     smplb200_model* m = const_cast<smplb200_model*>(cm);
     std::lock_guard<std::mutex> lock(m->mu);
-    CUDA_OK(cudaSetDevice(m->device));
+    DeviceGuard guard(m->device);
+    CUDA_OK(guard.err);
     if (!m->host_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->host_stream, cudaStreamNonBlocking));
     if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     if (!m->fit_done) CUDA_OK(cudaEventCreateWithFlags(&m->fit_done, cudaEventDisableTiming));

@@ -381,6 +381,61 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
 }
 
 // --------------------------------------------------------------------------------------------------
+// The three prior terms of body_fitting_loss on their own (smplify/losses.py:46-52: 4.78^2 * MaxMixturePrior
+// (smplify/prior.py:181-196) + 15.2^2 * angle_prior (losses.py:19-24) + 5^2 * |betas|^2) with their gradients, through the
+// SAME tile phases the fit kernel runs every iteration - the isolated check of rows a15, a16 (prior part), a19.
+// --------------------------------------------------------------------------------------------------
+struct PriorParams {
+    int batch;
+    const float* pose;        // [B][72] full pose (global orientation first; the prior reads entries 3..71)
+    const float* betas;       // [B][10]
+    float* terms;             // [B][3]  weighted pose prior, angle prior, shape prior
+    float* components;        // [B][8]  0.5 d^T P d - log(nll_weight) of every mixture component (nullable)
+    int* argmin;              // [B]     selected component (nullable)
+    float* grad_body_pose;    // [B][69] d(sum of the three terms)/d body_pose (nullable)
+    float* grad_betas;        // [B][10] (nullable)
+};
+
+template <int S>
+SB_HD void prior_tile(const ModelView& M, const PriorParams& P, int first, float* sm) {
+    using L = TileLayout<S>;
+    const SmallConsts C = stage_small_consts<S>(M, sm);
+    FOR_ITEMS(it, S * 72) {
+        const int s = it / 72, k = it % 72, b = first + s;
+        sm[L::POSE + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 72 + k] : 0.f;
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, k = it % kBetas, b = first + s;
+        sm[L::BETA + k * S + s] = (b < P.batch) ? P.betas[(size_t)b * kBetas + k] : 0.f;
+    }
+    TILE_SYNC();
+    ph_prior_quadratic<S>(M, C, sm);
+    TILE_SYNC();
+    ph_prior_select<S>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
+    TILE_SYNC();
+    FOR_ITEMS(it, S * 3) {
+        const int s = it / 3, k = it % 3, b = first + s;
+        if (b < P.batch) P.terms[(size_t)b * 3 + k] = sm[L::LOSSJ + (49 + k) * S + s];
+    }
+    FOR_ITEMS(it, S * kGauss) {
+        const int s = it / kGauss, g = it % kGauss, b = first + s;
+        if (P.components && b < P.batch) P.components[(size_t)b * kGauss + g] = sm[L::MISC + g * S + s];
+    }
+    FOR_ITEMS(s, S) {
+        const int b = first + s;
+        if (P.argmin && b < P.batch) P.argmin[b] = (int)sm[L::MISC + 8 * S + s];
+    }
+    FOR_ITEMS(it, S * kPriorDim) {
+        const int s = it / kPriorDim, i = it % kPriorDim, b = first + s;
+        if (P.grad_body_pose && b < P.batch) P.grad_body_pose[(size_t)b * kPriorDim + i] = sm[L::GPR + i * S + s];
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, l = it % kBetas, b = first + s;
+        if (P.grad_betas && b < P.batch) P.grad_betas[(size_t)b * kBetas + l] = 2.f * kShapePriorW2 * sm[L::BETA + l * S + s];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // SMPL.forward / backward, per-sample half
 // --------------------------------------------------------------------------------------------------
 struct PoseParams {

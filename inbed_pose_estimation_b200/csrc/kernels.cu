@@ -44,10 +44,30 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(const __grid
 }
 
 template <int S>
+__global__ void __launch_bounds__(kPoseThreads) prior_terms_kernel(const __grid_constant__ ModelView M,
+                                                                   const __grid_constant__ PriorParams P) {
+    extern __shared__ __align__(16) float sm[];
+    prior_tile<S>(M, P, blockIdx.x * S, sm);
+}
+
+template <int S>
 __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(const __grid_constant__ ModelView M,
                                                                      const __grid_constant__ PoseParams P) {
     extern __shared__ __align__(16) float sm[];
     pose_backward_tile<S>(M, P, blockIdx.x * S, sm);
+}
+
+// SM count of the CURRENT device, cached per device index (a process may drive several GPUs).
+int device_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev];
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;                                  // benign race: every thread writes the same value
+    }
+    return n;
 }
 
 template <int S>
@@ -112,11 +132,7 @@ cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stre
     if (variant == 4) return launch_fit_variant<12, 384, 1>(M, P, stream);
     if (variant == 6) return launch_fit_variant<8, 384, 1>(M, P, stream);
     if (variant == 7) return launch_fit_variant<4, 384, 1>(M, P, stream);
-    static const int sms = [] {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n > 0 ? n : 148;
-    }();
+    const int sms = device_sm_count();
     int n16 = 0, small = 0, n_small = 0;
     plan_fit_tiles(P.batch, sms, &n16, &small, &n_small);
     if (n16 == 0) {
@@ -143,6 +159,20 @@ static cudaError_t launch_pose_backward_s(const ModelView& M, const PoseParams& 
     if (e != cudaSuccess) return e;
     pose_backward_kernel<S><<<(P.batch + S - 1) / S, kPoseThreads, tile_smem_bytes<S>(), stream>>>(M, P);
     return cudaGetLastError();
+}
+
+template <int S>
+static cudaError_t launch_prior_terms_s(const ModelView& M, const PriorParams& P, cudaStream_t stream) {
+    cudaError_t e = opt_in_smem(prior_terms_kernel<S>, tile_smem_bytes<S>());
+    if (e != cudaSuccess) return e;
+    prior_terms_kernel<S><<<(P.batch + S - 1) / S, kPoseThreads, tile_smem_bytes<S>(), stream>>>(M, P);
+    return cudaGetLastError();
+}
+// Both GEMM forms of the prior phase the fit kernel uses are reachable: the K-split form of the one-group tiles (S = 8) and
+// the two-sample-group form of the 16-sample tiles.
+cudaError_t launch_prior_terms(const ModelView& M, const PriorParams& P, cudaStream_t stream) {
+    if (P.batch <= 0) return cudaSuccess;
+    return P.batch >= 16 * 128 ? launch_prior_terms_s<16>(M, P, stream) : launch_prior_terms_s<8>(M, P, stream);
 }
 
 // 16 samples per CTA halve the folded-basis bytes streamed from L2 per sample; small batches use 8 to fill more SMs.
@@ -220,11 +250,13 @@ cudaError_t launch_quat_rodrigues_bwd(const float* theta, const float* grot, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// utils/geometry.py:79-107  perspective_projection forward / backward
+// utils/geometry.py:79-114  perspective_projection forward / backward.  out_3d (:108-114; callers train/trainer.py:621-626,
+// models/hmr.py:1720, eval.py:255): a third channel holds the camera-space depth (row 2 of K applied to the un-normalised
+// point), the first two are unchanged.
 // ------------------------------------------------------------------------------------------------
 __global__ void projection_fwd_kernel(const float* __restrict__ pts, const float* __restrict__ rot, const float* __restrict__ tr,
                                       const float* __restrict__ focal, int focal_per_batch, const float* __restrict__ cen,
-                                      float* __restrict__ out, int batch, int npts) {
+                                      float* __restrict__ out, int out_3d, int batch, int npts) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)batch * npts) return;
     const int b = (int)(i / npts);
@@ -234,14 +266,16 @@ __global__ void projection_fwd_kernel(const float* __restrict__ pts, const float
     const float Py = (R[3] * X + R[4] * Y + R[5] * Z) + tr[3 * b + 1];
     const float Pz = (R[6] * X + R[7] * Y + R[8] * Z) + tr[3 * b + 2];
     const float f = focal[focal_per_batch ? b : 0];
-    out[2 * i + 0] = f * (Px / Pz) + cen[2 * b + 0];
-    out[2 * i + 1] = f * (Py / Pz) + cen[2 * b + 1];
+    const size_t o = (out_3d ? 3 : 2) * i;
+    out[o + 0] = f * (Px / Pz) + cen[2 * b + 0];
+    out[o + 1] = f * (Py / Pz) + cen[2 * b + 1];
+    if (out_3d) out[o + 2] = Pz;
 }
 
 // one CTA per batch element; d_rot / d_tr are reduced over the points in shared memory
 __global__ void __launch_bounds__(128) projection_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ rot,
                                                              const float* __restrict__ tr, const float* __restrict__ focal,
-                                                             int focal_per_batch, const float* __restrict__ gout,
+                                                             int focal_per_batch, const float* __restrict__ gout, int out_3d,
                                                              float* __restrict__ gpts, float* __restrict__ grot,
                                                              float* __restrict__ gtr, int npts) {
     __shared__ float red[4][12];
@@ -257,8 +291,9 @@ __global__ void __launch_bounds__(128) projection_bwd_kernel(const float* __rest
         const float Px = (R[0] * X + R[1] * Y + R[2] * Z) + tr[3 * b + 0];
         const float Py = (R[3] * X + R[4] * Y + R[5] * Z) + tr[3 * b + 1];
         const float Pz = (R[6] * X + R[7] * Y + R[8] * Z) + tr[3 * b + 2];
-        const float gu = gout[2 * i] * f, gv = gout[2 * i + 1] * f;
-        const float dP[3] = {gu / Pz, gv / Pz, -(gu * (Px / Pz) + gv * (Py / Pz)) / Pz};
+        const size_t go = (out_3d ? 3 : 2) * i;
+        const float gu = gout[go] * f, gv = gout[go + 1] * f;
+        const float dP[3] = {gu / Pz, gv / Pz, -(gu * (Px / Pz) + gv * (Py / Pz)) / Pz + (out_3d ? gout[go + 2] : 0.f)};
         gpts[3 * i + 0] = R[0] * dP[0] + R[3] * dP[1] + R[6] * dP[2];
         gpts[3 * i + 1] = R[1] * dP[0] + R[4] * dP[1] + R[7] * dP[2];
         gpts[3 * i + 2] = R[2] * dP[0] + R[5] * dP[1] + R[8] * dP[2];
@@ -284,16 +319,18 @@ __global__ void __launch_bounds__(128) projection_bwd_kernel(const float* __rest
 }
 
 cudaError_t launch_projection_fwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,
-                                  const float* cen, float* out, int batch, int npts, cudaStream_t st) {
+                                  const float* cen, float* out, int out_3d, int batch, int npts, cudaStream_t st) {
     const size_t n = (size_t)batch * npts;
     if (n == 0) return cudaSuccess;
-    projection_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, rot, tr, focal, focal_per_batch, cen, out, batch, npts);
+    projection_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pts, rot, tr, focal, focal_per_batch, cen, out, out_3d, batch,
+                                                                       npts);
     return cudaGetLastError();
 }
 cudaError_t launch_projection_bwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,
-                                  const float* gout, float* gpts, float* grot, float* gtr, int batch, int npts, cudaStream_t st) {
+                                  const float* gout, int out_3d, float* gpts, float* grot, float* gtr, int batch, int npts,
+                                  cudaStream_t st) {
     if (batch <= 0) return cudaSuccess;
-    projection_bwd_kernel<<<batch, 128, 0, st>>>(pts, rot, tr, focal, focal_per_batch, gout, gpts, grot, gtr, npts);
+    projection_bwd_kernel<<<batch, 128, 0, st>>>(pts, rot, tr, focal, focal_per_batch, gout, out_3d, gpts, grot, gtr, npts);
     return cudaGetLastError();
 }
 

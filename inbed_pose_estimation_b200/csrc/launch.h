@@ -7,30 +7,35 @@ namespace smplb200 {
 
 struct FitParams;
 struct PoseParams;
+struct PriorParams;
 
 constexpr int kFitThreads = 384;
 constexpr int kPoseThreads = 384;
 
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream);
 void plan_fit_tiles(int batch, int sms, int* n16, int* small, int* n_small);
+int device_sm_count();      // of the current device (cached per device index)
+cudaError_t launch_prior_terms(const ModelView& M, const PriorParams& P, cudaStream_t stream);
 cudaError_t launch_pose_forward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
 cudaError_t launch_pose_backward(const ModelView& M, const PoseParams& P, cudaStream_t stream);
 cudaError_t launch_quat_rodrigues_fwd(const float* theta, float* rot, int n, cudaStream_t st);
 cudaError_t launch_quat_rodrigues_bwd(const float* theta, const float* grot, float* gtheta, int n, cudaStream_t st);
 cudaError_t launch_projection_fwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,
-                                  const float* cen, float* out, int batch, int npts, cudaStream_t st);
+                                  const float* cen, float* out, int out_3d, int batch, int npts, cudaStream_t st);
 cudaError_t launch_projection_bwd(const float* pts, const float* rot, const float* tr, const float* focal, int focal_per_batch,
-                                  const float* gout, float* gpts, float* grot, float* gtr, int batch, int npts, cudaStream_t st);
+                                  const float* gout, int out_3d, float* gpts, float* grot, float* gtr, int batch, int npts,
+                                  cudaStream_t st);
 
 // adjacent.cu: the steps either side of SMPLify in the reference's train step
 cudaError_t launch_rot6d_to_rotmat(const float* x, float* R, int n, cudaStream_t st);
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, int scrub_nan, cudaStream_t st);
 cudaError_t launch_estimate_translation(const float* S, const float* kp, float focal, float img_size, float* trans, int batch,
                                         cudaStream_t st);
-cudaError_t launch_fits_get(const float* store, const long long* index, const float* rot, const uint8_t* flipped, const int* perm72,
-                            float* pose, float* betas, int batch, cudaStream_t st);
-cudaError_t launch_fits_set(float* store, const long long* index, const float* rot, const uint8_t* flipped, const uint8_t* update,
-                            const int* perm72, const float* pose, const float* betas, int batch, cudaStream_t st);
+cudaError_t launch_fits_get(const float* store, long long store_rows, const long long* index, const float* rot, const uint8_t* flipped,
+                            const int* perm72, float* pose, float* betas, int* status, int batch, cudaStream_t st);
+cudaError_t launch_fits_set(float* store, long long store_rows, const long long* index, const float* rot, const uint8_t* flipped,
+                            const uint8_t* update, const int* perm72, const float* pose, const float* betas, int* status, int batch,
+                            cudaStream_t st);
 cudaError_t launch_keep_better(const float* new_reproj, const float* new_pose, const float* new_betas, const float* new_cam,
                                const float* new_joints, float* loss, float* pose, float* betas, float* cam, float* joints,
                                uint8_t* update, int batch, cudaStream_t st);

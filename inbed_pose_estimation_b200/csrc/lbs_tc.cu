@@ -706,15 +706,7 @@ bool tc_make_constant_maps(TcConstMaps* m, const float* basisT_hi, const float* 
            make_map(&m->wT_hi, wT_hi, kTcVertRowsPad, 32, 0, 32) && make_map(&m->wT_lo, wT_lo, kTcVertRowsPad, 32, 0, 32);
 }
 
-static int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
-}
+static int sm_count() { return device_sm_count(); }      // kernels.cu: cached per device
 
 template <typename K>
 static cudaError_t opt_in(K kernel, uint32_t bytes) {

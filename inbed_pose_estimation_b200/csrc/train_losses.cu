@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) shape_loss_kernel(const float2* __restric
                                                          const uint8_t* __restrict__ valid, double* __restrict__ ws,
                                                          float2* __restrict__ grad_pred) {
     __shared__ double red[8];
-    const int b = blockIdx.y, ch = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.x / kShapeChunks, ch = blockIdx.x % kShapeChunks, t = threadIdx.x;   // batch in gridDim.x: no 65 535 cap
     const bool on = valid[b] != 0;
     const size_t base = (size_t)b * (kVertFloats / 2) + (size_t)ch * kChunkPairs;
     float acc = 0.f;
@@ -280,7 +280,7 @@ cudaError_t launch_shape_loss(int batch, const float* pred, const float* gt, con
                               double* ws, cudaStream_t st) {
     mask_count_kernel<<<1, 1024, 0, st>>>(valid, batch, ws);
     if (batch > 0)
-        shape_loss_kernel<<<dim3(kShapeChunks, batch), 256, 0, st>>>(reinterpret_cast<const float2*>(pred),
+        shape_loss_kernel<<<(unsigned)batch * kShapeChunks, 256, 0, st>>>(reinterpret_cast<const float2*>(pred),
                                                                      reinterpret_cast<const float2*>(gt), valid, ws,
                                                                      reinterpret_cast<float2*>(grad_pred));
     loss_reduce_kernel<<<1, 256, 0, st>>>(ws, batch * kShapeChunks, 1, (float)kVertFloats, (float)kVertFloats, loss);

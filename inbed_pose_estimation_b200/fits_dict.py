@@ -2,7 +2,8 @@
 
 The reference keeps one CPU tensor [N, 82] (72 pose + 10 betas) per dataset and, on every get / set, loops over the
 batch in Python and calls cv2.Rodrigues per sample.  Here the store lives in HBM and each call is one kernel:
-gather + rotate + flip (__getitem__), un-flip + un-rotate + masked scatter (__setitem__).  The on-disk format is
+gather + rotate + flip (__getitem__), un-flip + un-rotate + masked scatter (__setitem__); index bounds are validated
+inside the kernel and reported through a device flag, so neither call synchronises with the host.  The on-disk format is
 unchanged (<checkpoint_dir>/<dataset>_fits.npy, falling back to config.STATIC_FITS_DIR).
 """
 import ctypes
@@ -24,48 +25,71 @@ def _u8(t, dev):
     return torch.as_tensor(t).to(dev).to(torch.uint8).contiguous()
 
 
-def fits_get(store, index, rot, is_flipped):
-    """store [N,82] (CUDA) -> (pose [B,72], betas [B,10]) for rows `index`, rotated by `rot` degrees then flipped."""
+def _status_flag(dev):
+    return torch.zeros(1, device=dev, dtype=torch.int32)
+
+
+def check_status(status):
+    """Raise IndexError if any fits_get / fits_set call that was given `status` saw an out-of-range index.  This is the
+    one host synchronisation of the bounds check; call it whenever convenient (FitsDict does so in save())."""
+    if status is not None and int(status.item()) != 0:
+        status.zero_()
+        raise IndexError('fits index out of range')
+
+
+def fits_get(store, index, rot, is_flipped, status=None):
+    """store [N,82] (CUDA) -> (pose [B,72], betas [B,10]) for rows `index`, rotated by `rot` degrees then flipped.
+    Indices are checked on the device: rows outside [0, N) come back as NaN and raise `status` (an int32 device tensor,
+    see check_status); without `status` the check is made here, at the cost of a host synchronisation."""
     dev = store.device
     if dev.type != 'cuda':
         raise RuntimeError('FitsDict store must live on a CUDA device (no CPU fallback)')
-    idx = torch.as_tensor(index).to(dev).to(torch.int64).contiguous()
+    idx = torch.as_tensor(index).to(dev, torch.int64, non_blocking=True).contiguous()
     B = idx.shape[0]
-    r = torch.as_tensor(rot).to(dev).float().contiguous()
+    r = torch.as_tensor(rot).to(dev, torch.float32, non_blocking=True).contiguous()
     f = _u8(is_flipped, dev)
     pose = torch.empty((B, 72), device=dev, dtype=torch.float32)
     betas = torch.empty((B, 10), device=dev, dtype=torch.float32)
     if B:
-        if int(idx.min()) < 0 or int(idx.max()) >= store.shape[0]:
-            raise IndexError('fits index out of range')
+        flag = status if status is not None else _status_flag(dev)
         with torch.cuda.device(dev):
             _native.check(_native.lib().smplb200_fits_get(
-                B, _native.ptr(store), ctypes.c_void_p(idx.data_ptr()), _native.ptr(r), ctypes.c_void_p(f.data_ptr()), _perm_ptr(),
-                _native.ptr(pose), _native.ptr(betas), torch.cuda.current_stream(dev).cuda_stream))
+                B, _native.ptr(store), int(store.shape[0]), ctypes.c_void_p(idx.data_ptr()), _native.ptr(r),
+                ctypes.c_void_p(f.data_ptr()), _perm_ptr(), _native.ptr(pose), _native.ptr(betas), ctypes.c_void_p(flag.data_ptr()),
+                torch.cuda.current_stream(dev).cuda_stream))
+        if status is None:
+            check_status(flag)
     return pose, betas
 
 
-def fits_set(store, index, rot, is_flipped, update, pose, betas):
-    """Undo flip and rotation of (pose, betas) and overwrite the rows of `store` where `update` is set."""
+def fits_set(store, index, rot, is_flipped, update, pose, betas, status=None):
+    """Undo flip and rotation of (pose, betas) and overwrite the rows of `store` where `update` is set.  Out-of-range rows
+    are skipped and reported through `status` like in fits_get."""
     dev = store.device
-    idx = torch.as_tensor(index).to(dev).to(torch.int64).contiguous()
+    idx = torch.as_tensor(index).to(dev, torch.int64, non_blocking=True).contiguous()
     B = idx.shape[0]
     if not B:
         return
-    if int(idx.min()) < 0 or int(idx.max()) >= store.shape[0]:
-        raise IndexError('fits index out of range')
-    r = torch.as_tensor(rot).to(dev).float().contiguous()
+    r = torch.as_tensor(rot).to(dev, torch.float32, non_blocking=True).contiguous()
     f, u = _u8(is_flipped, dev), _u8(update, dev)
     p = pose.detach().to(dev).float().contiguous()
     b = betas.detach().to(dev).float().contiguous()
+    flag = status if status is not None else _status_flag(dev)
     with torch.cuda.device(dev):
         _native.check(_native.lib().smplb200_fits_set(
-            B, _native.ptr(store), ctypes.c_void_p(idx.data_ptr()), _native.ptr(r), ctypes.c_void_p(f.data_ptr()),
-            ctypes.c_void_p(u.data_ptr()), _perm_ptr(), _native.ptr(p), _native.ptr(b), torch.cuda.current_stream(dev).cuda_stream))
+            B, _native.ptr(store), int(store.shape[0]), ctypes.c_void_p(idx.data_ptr()), _native.ptr(r), ctypes.c_void_p(f.data_ptr()),
+            ctypes.c_void_p(u.data_ptr()), _perm_ptr(), _native.ptr(p), _native.ptr(b), ctypes.c_void_p(flag.data_ptr()),
+            torch.cuda.current_stream(dev).cuda_stream))
+    if status is None:
+        check_status(flag)
 
 
 class FitsDict(object):
-    """ Dictionary keeping track of the best fit per image in the training set (device resident). """
+    """ Dictionary keeping track of the best fit per image in the training set (device resident).
+
+    All datasets share ONE device store (their rows back to back; `fits_dict[name]` is a view of its rows), so a mixed
+    batch is one kernel launch: the per-dataset row offset is added to the indices on the host, where the dataset names
+    live anyway.  Index bounds are checked inside the kernels; the sticky device flag is read by check() / save(). """
 
     def __init__(self, options, train_dataset, device=torch.device('cuda'), fits=None):
         """`fits`: optional {dataset name: array [N, 82]} to use instead of the .npy files."""
@@ -77,6 +101,7 @@ class FitsDict(object):
         self.fits_dict = {}
         self.flipped_parts = torch.tensor(constants.SMPL_POSE_FLIP_PERM, dtype=torch.int64)
         names = list(fits.keys()) if fits is not None else list(train_dataset.dataset_dict.keys())
+        arrays = []
         for ds_name in names:
             if fits is not None:
                 arr = np.asarray(fits[ds_name], dtype=np.float32)
@@ -88,55 +113,56 @@ class FitsDict(object):
                     arr = np.load(os.path.join(config.STATIC_FITS_DIR, ds_name + '_fits.npy'))
             if arr.ndim != 2 or arr.shape[1] != 82:
                 raise ValueError('%s fits must be [N, 82]' % ds_name)
-            self.fits_dict[ds_name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
+            arrays.append(np.ascontiguousarray(arr, dtype=np.float32))
+        self._offset, self._rows = {}, {}
+        row = 0
+        for ds_name, arr in zip(names, arrays):
+            self._offset[ds_name], self._rows[ds_name] = row, arr.shape[0]
+            row += arr.shape[0]
+        self._store = torch.from_numpy(np.concatenate(arrays, axis=0) if arrays else np.zeros((0, 82), np.float32)).to(self.device)
+        for ds_name in names:
+            self.fits_dict[ds_name] = self._store[self._offset[ds_name]:self._offset[ds_name] + self._rows[ds_name]]
+        self._status = _status_flag(self.device)
+
+    def check(self):
+        """Raise IndexError if a get / set since the last check used an index outside its dataset (one host sync)."""
+        check_status(self._status)
 
     def save(self):
         """ Save dictionary state to disk """
+        self.check()
         for ds_name, store in self.fits_dict.items():
             np.save(os.path.join(self.options.checkpoint_dir, ds_name + '_fits.npy'), store.cpu().numpy())
 
-    def _groups(self, dataset_name):
-        groups = {}
-        for n, ds in enumerate(dataset_name):
-            groups.setdefault(ds, []).append(n)
-        return groups
+    def _global_index(self, dataset_name, ind):
+        """Row of the shared store for every (dataset, index) pair; -1 where the index leaves its dataset, so that the
+        kernel's bounds check reports it (host arithmetic on host data: the names are Python strings)."""
+        ind = np.asarray(torch.as_tensor(ind).cpu(), dtype=np.int64).reshape(-1)
+        off = np.fromiter((self._offset[d] for d in dataset_name), dtype=np.int64, count=len(dataset_name))
+        rows = np.fromiter((self._rows[d] for d in dataset_name), dtype=np.int64, count=len(dataset_name))
+        return torch.from_numpy(np.where((ind >= 0) & (ind < rows), ind + off, -1))
 
     def __getitem__(self, x):
         """ Retrieve dictionary entries: (pose [B,72], betas [B,10]) on the store's device """
         dataset_name, ind, rot, is_flipped = x
-        B = len(dataset_name)
-        ind, rot = torch.as_tensor(ind), torch.as_tensor(rot)
-        flipped = torch.as_tensor(is_flipped)
-        pose = torch.empty((B, 72), device=self.device, dtype=torch.float32)
-        betas = torch.empty((B, 10), device=self.device, dtype=torch.float32)
-        for ds, rows in self._groups(dataset_name).items():
-            rows_t = torch.as_tensor(rows)
-            p, b = fits_get(self.fits_dict[ds], ind[rows_t], rot[rows_t], flipped[rows_t])
-            pose[rows_t.to(self.device)] = p
-            betas[rows_t.to(self.device)] = b
-        return pose, betas
+        return fits_get(self._store, self._global_index(dataset_name, ind), rot, is_flipped, status=self._status)
 
     def __setitem__(self, x, val):
         """ Update dictionary entries """
         dataset_name, ind, rot, is_flipped, update = x
         pose, betas = val
-        ind, rot = torch.as_tensor(ind), torch.as_tensor(rot)
-        flipped, update = torch.as_tensor(is_flipped), torch.as_tensor(update)
-        for ds, rows in self._groups(dataset_name).items():
-            rows_t = torch.as_tensor(rows)
-            rd = rows_t.to(pose.device)
-            fits_set(self.fits_dict[ds], ind[rows_t], rot[rows_t], flipped[rows_t], update[rows_t], pose[rd], betas[rd])
+        fits_set(self._store, self._global_index(dataset_name, ind), rot, is_flipped, update, pose, betas, status=self._status)
 
     def flip_pose(self, pose, is_flipped):
         """flip SMPL pose parameters (through the get kernel on a scratch store)"""
         B = pose.shape[0]
         store = torch.cat([pose.detach().to(self.device).float(), torch.zeros((B, 10), device=self.device)], dim=1).contiguous()
-        p, _ = fits_get(store, torch.arange(B), torch.zeros(B), is_flipped)
+        p, _ = fits_get(store, torch.arange(B), torch.zeros(B), is_flipped, status=self._status)
         return p
 
     def rotate_pose(self, pose, rot):
         """Rotate SMPL pose parameters by rot degrees"""
         B = pose.shape[0]
         store = torch.cat([pose.detach().to(self.device).float(), torch.zeros((B, 10), device=self.device)], dim=1).contiguous()
-        p, _ = fits_get(store, torch.arange(B), rot, torch.zeros(B, dtype=torch.uint8))
+        p, _ = fits_get(store, torch.arange(B), rot, torch.zeros(B, dtype=torch.uint8), status=self._status)
         return p

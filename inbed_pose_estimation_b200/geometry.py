@@ -1,7 +1,7 @@
 """Geometry ops of the hot path with the reference's signatures (utils/geometry.py), CUDA-backed.
 
 batch_rodrigues        - utils/geometry.py:9-23 (+ quat_to_rotmat :25-45)
-perspective_projection - utils/geometry.py:79-107
+perspective_projection - utils/geometry.py:79-114 (both the 2-D and the out_3d=True form)
 Both are differentiable (hand-written backward kernels) and CUDA only.
 """
 import torch
@@ -49,7 +49,7 @@ def batch_rodrigues(theta):
 
 class _Projection(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, rotation, translation, focal, center):
+    def forward(ctx, points, rotation, translation, focal, center, out_3d):
         B, N = points.shape[0], points.shape[1]
         dev = points.device
         p = points.detach().contiguous().float()
@@ -57,13 +57,13 @@ class _Projection(torch.autograd.Function):
         t = translation.detach().contiguous().float()
         c = center.detach().contiguous().float()
         per_batch = int(focal.numel() > 1)
-        out = torch.empty((B, N, 2), device=dev, dtype=torch.float32)
+        out = torch.empty((B, N, 3 if out_3d else 2), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _native.check(_native.lib().smplb200_perspective_projection(
-                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), per_batch, _native.ptr(c),
+                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), per_batch, _native.ptr(c), int(out_3d),
                 _native.ptr(out), _stream(dev)))
         ctx.save_for_backward(p, r, t, focal)
-        ctx.per_batch = per_batch
+        ctx.per_batch, ctx.out_3d, ctx.rot_shape = per_batch, bool(out_3d), tuple(rotation.shape)
         return out
 
     @staticmethod
@@ -74,25 +74,38 @@ class _Projection(torch.autograd.Function):
         gp, gr, gt = torch.empty_like(p), torch.empty_like(r), torch.empty_like(t)
         with torch.cuda.device(p.device):
             _native.check(_native.lib().smplb200_perspective_projection_backward(
-                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), ctx.per_batch, _native.ptr(g),
-                _native.ptr(gp), _native.ptr(gr), _native.ptr(gt), _stream(p.device)))
-        return gp, gr, gt, None, None
+                B, N, _native.ptr(p), _native.ptr(r), _native.ptr(t), _native.ptr(focal), ctx.per_batch, int(ctx.out_3d),
+                _native.ptr(g), _native.ptr(gp), _native.ptr(gr), _native.ptr(gt), _stream(p.device)))
+        if ctx.rot_shape != tuple(gr.shape):               # a broadcast rotation ([3,3] or [1,3,3]) gets the summed gradient
+            gr = gr.sum_to_size(ctx.rot_shape)
+        return gp, gr, gt, None, None, None
 
 
 def perspective_projection(points, rotation, translation, focal_length, camera_center, out_3d=False):
-    """points [B,N,3], rotation [B,3,3], translation [B,3], focal_length scalar or [B],
-    camera_center [B,2] -> [B,N,2].  (The reference's out_3d=True variant is off the hot path.)"""
-    if out_3d:
-        raise NotImplementedError('out_3d=True is not part of the hot path')
+    """points [B,N,3], rotation [B,3,3] (or broadcastable to it), translation [B,3], focal_length scalar or [B],
+    camera_center [B,2] -> [B,N,2]; with out_3d=True (reference utils/geometry.py:108-114; train/trainer.py:621-626,
+    models/hmr.py:1720) -> [B,N,3] whose third channel is the camera-space depth.  Differentiable w.r.t. points, rotation
+    and translation; the reference's callers pass constant intrinsics, so focal_length / camera_center that require grad
+    are rejected instead of silently getting none."""
     _require_cuda(points, 'perspective_projection')
+    if points.dim() != 3 or points.shape[2] != 3:
+        raise ValueError('points must be [B, N, 3]')
     B = points.shape[0]
+    if tuple(translation.shape) != (B, 3) or tuple(camera_center.shape) != (B, 2):
+        raise ValueError('translation must be [B, 3] and camera_center [B, 2]')
+    if rotation.dim() not in (2, 3) or tuple(rotation.shape[-2:]) != (3, 3) or (rotation.dim() == 3 and rotation.shape[0] not in (1, B)):
+        raise ValueError('rotation must be [B, 3, 3], [1, 3, 3] or [3, 3]')
     if torch.is_tensor(focal_length):
+        if focal_length.requires_grad:
+            raise NotImplementedError('perspective_projection: no gradient w.r.t. focal_length (constant intrinsics only)')
         focal = focal_length.detach().to(points.device, torch.float32).reshape(-1).contiguous()
         if focal.numel() not in (1, B):
             raise ValueError('focal_length must be a scalar or have one entry per batch element')
     else:
         focal = torch.full((1,), float(focal_length), device=points.device, dtype=torch.float32)
-    return _Projection.apply(points, rotation, translation, focal, camera_center)
+    if camera_center.requires_grad:
+        raise NotImplementedError('perspective_projection: no gradient w.r.t. camera_center (constant intrinsics only)')
+    return _Projection.apply(points, rotation, translation, focal, camera_center, bool(out_3d))
 
 
 # ---- the steps either side of SMPLify (SURVEY.md 8f) -----------------------------------------------------------------

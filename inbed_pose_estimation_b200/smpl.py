@@ -58,7 +58,6 @@ class _SMPLFunction(torch.autograd.Function):
     def forward(ctx, module, pose, betas, rotmat_mode, need_vertices):
         B = betas.shape[0]
         dev = betas.device
-        native = module.native(dev)
         lib = _native.lib()
         pose_c = pose.detach().contiguous().float()
         betas_c = betas.detach().contiguous().float()
@@ -68,8 +67,9 @@ class _SMPLFunction(torch.autograd.Function):
         # v_posed of the forward pass, kept for the backward call: [B][20736] (padded, 16-byte aligned rows - TMA target)
         vposed = (torch.empty((B, _native.VPOSED_PITCH), device=dev, dtype=torch.float32)
                   if (needs_grad and need_vertices) else None)
-        ws = module.workspace(dev, B)
         with torch.cuda.device(dev):
+            native = module.native(dev)              # first use creates the constant blob: on `dev`, not the current device
+            ws = module.workspace(dev, B)
             if B > 0:
                 _native.check(lib.smplb200_smpl_forward(
                     native.handle, B, int(rotmat_mode), _native.ptr(pose_c), _native.ptr(betas_c), _native.ptr(verts),
@@ -79,6 +79,7 @@ class _SMPLFunction(torch.autograd.Function):
         ctx.save_for_backward(pose_c, betas_c, vposed if vposed is not None else torch.empty(0, device=dev))
         ctx.has_vposed = vposed is not None
         ctx.wanted_vertices = bool(need_vertices)
+        ctx.set_materialize_grads(False)          # a joints-only loss must not run the vertex backward on a zero gradient
         if verts is None:
             verts = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(verts)
@@ -95,12 +96,14 @@ class _SMPLFunction(torch.autograd.Function):
         if g_verts is not None and g_verts.numel() > 0 and not ctx.has_vposed and ctx.wanted_vertices:
             raise RuntimeError('SMPL backward: vertex gradient arrived but v_posed was not saved')
         gj = g_joints.contiguous().float() if g_joints is not None else None
+        if gv is None and gj is None:              # neither output was used by the loss
+            return None, torch.zeros(ctx.pose_shape, device=dev), torch.zeros_like(betas_c), None, None
         d_pose = torch.empty_like(pose_c)
         d_betas = torch.empty_like(betas_c)
-        ws = module.workspace(dev, B)
         if B == 0:
             return None, d_pose.view(ctx.pose_shape), d_betas, None, None
         with torch.cuda.device(dev):
+            ws = module.workspace(dev, B)
             _native.check(lib.smplb200_smpl_backward(
                 module.native(dev).handle, B, int(ctx.rotmat_mode), _native.ptr(pose_c), _native.ptr(betas_c),
                 _native.ptr(vposed) if ctx.has_vposed else None, _native.ptr(gv), _native.ptr(gj),

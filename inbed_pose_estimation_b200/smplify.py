@@ -114,3 +114,25 @@ class SMPLify(object):
         if writeback is not None:
             writeback[:, self.ign_joints, 2] = 0.
         return reproj
+
+    def prior_terms(self, pose, betas):
+        """The three prior terms of body_fitting_loss (reference smplify/losses.py:46-52) evaluated on their own by the same
+        device code the fit runs every iteration.  pose [B,72], betas [B,10] -> dict with 'terms' [B,3] (weighted pose prior,
+        angle prior, shape prior), 'components' [B,8], 'argmin' [B] (int32), 'grad_body_pose' [B,69], 'grad_betas' [B,10].
+        Not part of the reference's surface: a diagnostic / test hook."""
+        import ctypes
+        B = pose.shape[0]
+        self._dev = pose.device
+        pose_c = self._prep(pose, (B, 72), 'pose')
+        betas_c = self._prep(betas, (B, 10), 'betas')
+        dev = self._dev
+        out = {'terms': torch.empty((B, 3), device=dev), 'components': torch.empty((B, 8), device=dev),
+               'argmin': torch.empty((B,), device=dev, dtype=torch.int32), 'grad_body_pose': torch.empty((B, 69), device=dev),
+               'grad_betas': torch.empty((B, 10), device=dev)}
+        if B:
+            with torch.cuda.device(dev):
+                _native.check(_native.lib().smplb200_prior_terms(
+                    self.smpl.native(dev).handle, B, _native.ptr(pose_c), _native.ptr(betas_c), _native.ptr(out['terms']),
+                    _native.ptr(out['components']), ctypes.c_void_p(out['argmin'].data_ptr()), _native.ptr(out['grad_body_pose']),
+                    _native.ptr(out['grad_betas']), torch.cuda.current_stream(dev).cuda_stream))
+        return out

@@ -9,8 +9,11 @@
  *  - every pointer marked "device" is a CUDA device pointer to contiguous row-major fp32 data;
  *    the caller owns all input, output and workspace buffers; the library owns only the
  *    immutable model-constant blob between model_create and model_destroy;
- *  - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*), has no
- *    hidden global state and is thread-compatible;
+ *  - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*) and is
+ *    thread-compatible; the only process-wide state is a per-device cache of the SM count.  Compute
+ *    calls run on the CALLER's current device (the one the model was created on); model_create,
+ *    model_destroy and smplify_fit_host switch to the model's device themselves and restore the
+ *    caller's current device before returning;
  *  - return value 0 = success; anything else is an error whose text smplb200_last_error()
  *    returns for the calling thread.  There is no CPU fallback: without a CUDA device
  *    model_create fails.
@@ -76,8 +79,10 @@ size_t smplb200_smpl_workspace_bytes(int batch);
 /* SMPLify.__call__ (smplify/smplify.py:40-136): two-stage fit, num_iters Adam steps per stage.
  * keypoints [B][49][3] is read AND its confidences at ign_joints are zeroed in place after the
  * camera stage, exactly like the reference (:105).  vertices / loss_trace may be NULL.
- * loss_trace [2*num_iters][B]: per-sample loss of every iteration (stage 1 then stage 2). */
-int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+ * loss_trace [2*num_iters][B]: per-sample loss of every iteration (stage 1 then stage 2).
+ * step_size is the Adam lr as a double: torch.optim.Adam divides the Python float by the bias
+ * correction in float64 before the fp32 cast (smplify.py:79,107), and so does the kernel. */
+int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, double step_size, float focal_length,
                          const float* init_pose /*device [B][72]*/, const float* init_betas /*device [B][10]*/,
                          const float* init_cam_t /*device [B][3]*/, const float* camera_center /*device [B][2]*/,
                          float* keypoints_2d /*device [B][49][3], in/out*/,
@@ -92,6 +97,15 @@ int smplb200_smplify_fitting_loss(const smplb200_model* model, int batch, float 
                                   const float* pose, const float* betas, const float* cam_t, const float* camera_center,
                                   float* keypoints_2d, float* reprojection_loss,
                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* The three prior terms of body_fitting_loss (smplify/losses.py:46-52) on their own, through the same device code the
+ * fit runs every iteration: terms[b] = { 4.78^2 * MaxMixturePrior(body_pose) (smplify/prior.py:181-196, merged
+ * max-mixture), 15.2^2 * sum angle_prior(body_pose) (losses.py:19-24), 5^2 * |betas|^2 }.  pose is the full [B][72]
+ * pose (entries 3..71 are the body pose).  Optional outputs (may be NULL): the 8 per-component values
+ * 0.5 d^T P d - log(nll_weight), the selected component, and the gradient of the sum of the three terms. */
+int smplb200_prior_terms(const smplb200_model* model, int batch, const float* pose /*[B][72]*/, const float* betas /*[B][10]*/,
+                         float* terms /*[B][3]*/, float* components /*[B][8]*/, int32_t* argmin /*[B]*/,
+                         float* grad_body_pose /*[B][69]*/, float* grad_betas /*[B][10]*/, void* stream);
 
 /* SMPL.forward (models/smpl.py:21-33 -> smplx lbs).  rotmat_mode 0: pose is axis-angle [B][72]
  * (global_orient ++ body_pose); 1: pose is [B][24][3][3] (pose2rot=False).  saved_vposed
@@ -116,14 +130,17 @@ int smplb200_smpl_backward(const smplb200_model* model, int batch, int rotmat_mo
 int smplb200_batch_rodrigues(int n, const float* theta /*[n][3]*/, float* rotmat /*[n][3][3]*/, void* stream);
 int smplb200_batch_rodrigues_backward(int n, const float* theta, const float* grad_rotmat, float* grad_theta, void* stream);
 
-/* utils/geometry.py:79-107 perspective_projection and its gradient.  focal_length is a device
- * pointer to 1 value (focal_per_batch = 0) or to [B] values (focal_per_batch = 1). */
+/* utils/geometry.py:79-114 perspective_projection and its gradient.  focal_length is a device
+ * pointer to 1 value (focal_per_batch = 0) or to [B] values (focal_per_batch = 1).  out_3d != 0
+ * is the reference's out_3d=True variant (:108-114; callers train/trainer.py:621-626,
+ * models/hmr.py:1720, eval.py:255): projected / grad_projected are then [B][N][3] with the
+ * camera-space depth of the point in the third channel. */
 int smplb200_perspective_projection(int batch, int num_points, const float* points, const float* rotation,
                                     const float* translation, const float* focal_length, int focal_per_batch,
-                                    const float* camera_center, float* projected /*[B][N][2]*/, void* stream);
+                                    const float* camera_center, int out_3d, float* projected /*[B][N][2 or 3]*/, void* stream);
 int smplb200_perspective_projection_backward(int batch, int num_points, const float* points, const float* rotation,
                                              const float* translation, const float* focal_length, int focal_per_batch,
-                                             const float* grad_projected, float* grad_points, float* grad_rotation,
+                                             int out_3d, const float* grad_projected, float* grad_points, float* grad_rotation,
                                              float* grad_translation, void* stream);
 
 /* train/trainer.py:187-199 (and :603-615, models/hmr.py:1708-1710, eval.py:245-247): weak-perspective camera
@@ -154,11 +171,15 @@ int smplb200_estimate_translation(int batch, const float* joints3d, const float*
 /* train/fits_dict.py:34-94 FitsDict.__getitem__ / __setitem__ on a device-resident store [N][82]
  * (72 pose + 10 betas per image): gather + rotate + flip, and un-flip + un-rotate + masked scatter.
  * index int64 [B], rot_deg fp32 [B], flipped / update uint8 [B], pose_flip_perm = the 72 entries of
- * constants.SMPL_POSE_FLIP_PERM (host pointer).  Rows of one batch must have distinct indices. */
-int smplb200_fits_get(int batch, const float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
-                      const int32_t* pose_flip_perm, float* pose /*[B][72]*/, float* betas /*[B][10]*/, void* stream);
-int smplb200_fits_set(int batch, float* store, const int64_t* index, const float* rot_deg, const uint8_t* flipped,
-                      const uint8_t* update, const int32_t* pose_flip_perm, const float* pose, const float* betas, void* stream);
+ * constants.SMPL_POSE_FLIP_PERM (host pointer).  Rows of one batch must have distinct indices.
+ * Indices are validated against store_rows INSIDE the kernel (no host synchronisation): an out-of-range row is
+ * returned as NaNs (get) or skipped (set) and bit 0 of *status (device int32, may be NULL) is raised. */
+int smplb200_fits_get(int batch, const float* store, int64_t store_rows, const int64_t* index, const float* rot_deg,
+                      const uint8_t* flipped, const int32_t* pose_flip_perm, float* pose /*[B][72]*/, float* betas /*[B][10]*/,
+                      int32_t* status, void* stream);
+int smplb200_fits_set(int batch, float* store, int64_t store_rows, const int64_t* index, const float* rot_deg,
+                      const uint8_t* flipped, const uint8_t* update, const int32_t* pose_flip_perm, const float* pose,
+                      const float* betas, int32_t* status, void* stream);
 
 /* train/trainer.py:716-727: update[b] = mean_j(new_reprojection_loss[b][j]) < best_loss[b]; where it holds the
  * best_* rows are overwritten by the new fit (best_joints / new_joints [B][49][3] may both be NULL). */
@@ -205,7 +226,7 @@ int smplb200_shape_loss(int batch, const float* pred_vertices, const float* gt_v
  * (pinned for best throughput); copies inputs to the device, runs the fit, copies the results
  * back and synchronises.  vertices may be NULL (they are then left on the device and not
  * copied).  This is the call timed as "e2e" by bench.py. */
-int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_iters, float step_size, float focal_length,
+int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_iters, double step_size, float focal_length,
                               const float* init_pose, const float* init_betas, const float* init_cam_t,
                               const float* camera_center, float* keypoints_2d,
                               float* vertices, float* joints, float* pose, float* betas, float* camera_translation,

@@ -168,8 +168,8 @@ def quaternion_rodrigues(theta):
                        dim=1).view(theta.shape[0], 3, 3)
 
 
-def project_points(points, rotation, translation, focal_length, camera_center):
-    """utils/geometry.py:79-107."""
+def project_points(points, rotation, translation, focal_length, camera_center, out_3d=False):
+    """utils/geometry.py:79-114 (out_3d: the third channel is row 2 of K applied to the un-normalised point = its depth)."""
     B = points.shape[0]
     K = torch.zeros([B, 3, 3], device=points.device, dtype=points.dtype)
     K[:, 0, 0] = focal_length
@@ -180,7 +180,10 @@ def project_points(points, rotation, translation, focal_length, camera_center):
     points = points + translation.unsqueeze(1)
     proj = points / points[:, :, -1].unsqueeze(-1)
     proj = torch.einsum('bij,bkj->bki', K, proj)
-    return proj[:, :, :-1]
+    if not out_3d:
+        return proj[:, :, :-1]
+    proj[:, :, -1] = torch.einsum('bij,bkj->bki', K, points)[:, :, -1]
+    return proj
 
 
 # ----------------------------------------------------------------------------------------
@@ -325,9 +328,9 @@ class OracleSMPLify(object):
         return reproj
 
 
-def build_oracle(seed=0, dtype=torch.float32, num_iters=100):
+def build_oracle(seed=0, dtype=torch.float32, num_iters=100, structure='dense'):
     """Oracle SMPLify on the seeded synthetic model (same arrays the product loads)."""
     from inbed_pose_estimation_b200 import synthetic
-    smpl = OracleSMPL(synthetic.make_smpl_model(seed), synthetic.make_extra_regressor(seed + 1), dtype=dtype)
+    smpl = OracleSMPL(synthetic.make_smpl_model(seed, structure), synthetic.make_extra_regressor(seed + 1, structure), dtype=dtype)
     prior = OracleMaxMixturePrior(synthetic.make_gmm(seed + 2), dtype=dtype)
     return OracleSMPLify(smpl, prior, num_iters=num_iters)

@@ -11,7 +11,7 @@ from inbed_pose_estimation_b200 import _native, synthetic
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, 'libsmplify_emu.so')
-_vp, _ci, _cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_vp, _ci, _cf, _cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
 
 
 def available():
@@ -31,10 +31,10 @@ def _build():
         raise RuntimeError(res.stdout)
 
 
-def model_arrays(seed=0):
-    m = synthetic.make_smpl_model(seed)
+def model_arrays(seed=0, structure='dense'):
+    m = synthetic.make_smpl_model(seed, structure)
     arrays = {k: np.asarray(m[k], dtype=np.float32) for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights')}
-    arrays['J_regressor_extra'] = synthetic.make_extra_regressor(seed + 1)
+    arrays['J_regressor_extra'] = synthetic.make_extra_regressor(seed + 1, structure)
     arrays['parents'] = np.asarray(m['kintree_table'][0]).astype(np.int64)
     return arrays
 
@@ -49,17 +49,18 @@ def _p(a):
 
 
 class Emu(object):
-    def __init__(self, seed=0):
+    def __init__(self, seed=0, structure='dense', prior_seed=None):
         _build()
         self.lib = ctypes.CDLL(LIB)
         self.lib.emu_model_create.restype = _vp
         self.lib.emu_model_create.argtypes = [ctypes.POINTER(_native.ModelDesc)]
         self.lib.emu_last_error.restype = ctypes.c_char_p
-        self.lib.emu_fit.argtypes = [_vp, _ci, _ci, _cf, _cf, _ci] + [_vp] * 13
+        self.lib.emu_fit.argtypes = [_vp, _ci, _ci, _cd, _cf, _ci] + [_vp] * 13
+        self.lib.emu_prior.argtypes = [_vp, _ci] + [_vp] * 7
         self.lib.emu_pose.argtypes = [_vp, _ci, _ci, _ci] + [_vp] * 8 + [_ci, _vp, _vp]
         self.lib.emu_model_array.restype = ctypes.POINTER(ctypes.c_float)
         self.lib.emu_model_array.argtypes = [_vp, ctypes.c_char_p, ctypes.POINTER(_ci)]
-        desc, keep = _native.make_desc(model_arrays(seed), prior_arrays(seed))
+        desc, keep = _native.make_desc(model_arrays(seed, structure), prior_arrays(seed if prior_seed is None else prior_seed))
         self.model = self.lib.emu_model_create(ctypes.byref(desc))
         if not self.model:
             raise RuntimeError(self.lib.emu_last_error().decode())
@@ -83,6 +84,15 @@ class Emu(object):
                          _p(trace), _p(out['A']), _p(out['x']))
         out['trace'] = trace
         out['keypoints'] = kp
+        return out
+
+    def prior_terms(self, pose, betas):
+        B = pose.shape[0]
+        pose, betas = np.ascontiguousarray(pose, np.float32), np.ascontiguousarray(betas, np.float32)
+        out = {'terms': np.zeros((B, 3), np.float32), 'components': np.zeros((B, 8), np.float32), 'argmin': np.zeros(B, np.int32),
+               'grad_body_pose': np.zeros((B, 69), np.float32), 'grad_betas': np.zeros((B, 10), np.float32)}
+        self.lib.emu_prior(self.model, B, _p(pose), _p(betas), _p(out['terms']), _p(out['components']), _p(out['argmin']),
+                           _p(out['grad_body_pose']), _p(out['grad_betas']))
         return out
 
     def pose_forward(self, pose, betas, rotmat_mode=False):

@@ -64,7 +64,7 @@ struct Operands {
 
 static std::vector<float> tile_scratch() { return std::vector<float>(TileLayout<S>::SMEM_FLOATS + 64, 0.f); }
 
-extern "C" int emu_fit(EmuModel* m, int batch, int num_iters, float step_size, float focal, int loss_only,
+extern "C" int emu_fit(EmuModel* m, int batch, int num_iters, double step_size, float focal, int loss_only,
                        const float* pose, const float* betas, const float* cam, const float* center, float* kp,
                        float* joints, float* opose, float* obetas, float* ocam, float* reproj, float* trace,
                        float* ws_A, float* ws_x) {
@@ -76,7 +76,7 @@ extern "C" int emu_fit(EmuModel* m, int batch, int num_iters, float step_size, f
     Operands ops(batch);
     P.tc = ops.tc;
     P.loss_trace = trace;
-    P.lr = (double)step_size; P.beta1 = 0.9; P.beta2 = 0.999;
+    P.lr = step_size; P.beta1 = 0.9; P.beta2 = 0.999;
     P.adam_c.lerp_w = (float)(1.0 - 0.9); P.adam_c.beta2 = (float)0.999; P.adam_c.w2 = (float)(1.0 - 0.999); P.adam_c.eps = 1e-8f;
     std::vector<float> sm = tile_scratch();
     for (int t = 0; t < (batch + S - 1) / S; ++t) fit_tile<S>(m->H.view, P, t * S, sm.data());
@@ -108,6 +108,17 @@ extern "C" int emu_pose(EmuModel* m, int batch, int rotmat_mode, int backward, c
         else pose_forward_tile<S>(m->H.view, P, t * S, sm.data());
     }
     if (!backward) ops.unpack(batch, ws_A, ws_x);
+    return 0;
+}
+
+extern "C" int emu_prior(EmuModel* m, int batch, const float* pose, const float* betas, float* terms, float* components, int* argmin,
+                         float* grad_body_pose, float* grad_betas) {
+    PriorParams P;
+    memset(&P, 0, sizeof(P));
+    P.batch = batch; P.pose = pose; P.betas = betas; P.terms = terms; P.components = components; P.argmin = argmin;
+    P.grad_body_pose = grad_body_pose; P.grad_betas = grad_betas;
+    std::vector<float> sm = tile_scratch();
+    for (int t = 0; t < (batch + S - 1) / S; ++t) prior_tile<S>(m->H.view, P, t * S, sm.data());
     return 0;
 }
 

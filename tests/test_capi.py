@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), 'missing export ' + n
     assert sorted(_native.EXPORTED_SYMBOLS) == names
-    assert _native.lib().smplb200_version() == 100
+    assert _native.lib().smplb200_version() == 200
 
 
 def test_model_create_fails_loudly_without_gpu():

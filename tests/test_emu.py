@@ -136,3 +136,49 @@ def test_fit_beyond_the_on_chip_adam_table(emu):
     np.testing.assert_allclose(out['trace'].astype(np.float64).sum(1), tr_o, rtol=1e-5)
     np.testing.assert_allclose(out['pose'], ref[2].numpy(), atol=1e-4)
     np.testing.assert_allclose(out['cam_t'], ref[4].numpy(), atol=1e-4)
+
+
+def _check_prior_terms(out, g):
+    """Prior terms of one evaluation against the reference-run vectors of tests/golden/prior_near_tie.npz."""
+    assert np.array_equal(out['argmin'], g['argmin'])                    # same arg-min although the two best are ~1e-6 apart
+    np.testing.assert_allclose(out['components'], g['components'], rtol=1e-6)
+    np.testing.assert_allclose(out['terms'][:, 0], 4.78 ** 2 * g['nll'], rtol=2e-6)
+    np.testing.assert_allclose(out['terms'][:, 1], 15.2 ** 2 * g['angle'], rtol=2e-6)
+    np.testing.assert_allclose(out['terms'][:, 2], 25. * g['shape'], rtol=2e-6)
+    scale = np.abs(g['grad_body_pose']).max()
+    np.testing.assert_allclose(out['grad_body_pose'], g['grad_body_pose'], rtol=1e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(out['grad_betas'], g['grad_betas'], rtol=1e-6)
+
+
+def test_prior_terms_and_near_tie_argmin(emu):
+    """Rows a15 / a16 (prior part) / a19 in isolation: max-mixture prior, angle prior, shape prior and their gradients at
+    poses where two mixture components are within 3e-6 .. 1e-5 (relative) of each other."""
+    g = golden('prior_near_tie.npz')
+    assert g['rel_gap'].min() < 4e-6
+    pose = np.concatenate([np.zeros((len(g['body_pose']), 3), np.float32), g['body_pose']], axis=1)
+    _check_prior_terms(emu.prior_terms(pose, g['betas']), g)
+    # the round-1 vectors (random poses, no tie): value and gradient of the GMM term alone
+    g1 = golden('prior.npz')
+    pose1 = np.concatenate([np.zeros((16, 3), np.float32), g1['body_pose']], axis=1)
+    out = emu.prior_terms(pose1, np.zeros((16, 10), np.float32))
+    np.testing.assert_allclose(out['terms'][:, 0], 4.78 ** 2 * g1['nll'], rtol=2e-6)
+
+
+@pytest.mark.parametrize('variant', ['default', 'slp'])
+def test_fit_on_sparse_structured_model(variant):
+    """The folded constants (Cf, wkj, sigma_src, J0/JS) built from a SPARSE model - <= 10 vertices per regressor row, <= 4
+    skinning weights per vertex, exact zeros, extra-regressor rows that do not sum to 1 - against the reference's own run."""
+    g = golden('smplify_sparse_%s.npz' % variant)
+    e = emu_mod.Emu(seed=int(g['model_seed']), structure='sparse')
+    inp = {k: g[k] for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')}
+    out = e.fit(inp, num_iters=100)
+    np.testing.assert_allclose(out['trace'].astype(np.float64).sum(axis=1), g['loss_trace'], rtol=1e-5)
+    np.testing.assert_allclose(out['pose'], g['out_pose'], atol=1e-4)
+    np.testing.assert_allclose(out['betas'], g['out_betas'], atol=1e-4)
+    np.testing.assert_allclose(out['cam_t'], g['out_cam_t'], atol=1e-4)
+    np.testing.assert_allclose(out['joints'], g['out_joints'], atol=1e-4)
+    fs = golden('smpl_forward_sparse.npz')
+    joints, A, x = e.pose_forward(fs['pose'], fs['betas'])
+    np.testing.assert_allclose(joints, fs['joints'], atol=2e-6)
+    d_pose, d_betas = e.pose_backward(fs['pose'], fs['betas'], d_joints=fs['grad_joints'])
+    assert np.all(np.isfinite(d_pose)) and np.all(np.isfinite(d_betas))

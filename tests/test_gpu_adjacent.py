@@ -98,6 +98,37 @@ def test_fits_dict_class_round_trip(tmp_path):
     assert fd.flipped_parts.tolist() == constants.SMPL_POSE_FLIP_PERM
 
 
+def test_fits_index_bounds_checked_on_the_device(tmp_path):
+    """Out-of-range indices never touch memory outside the store: the get returns NaN rows, the set skips them, and the
+    sticky device flag turns into an IndexError at the next check (FitsDict.check / save, or at once without a flag)."""
+    gen = torch.Generator().manual_seed(6)
+    arr = torch.randn(50, 82, generator=gen).numpy()
+    store = torch.from_numpy(arr.copy()).cuda()
+    idx = torch.tensor([3, 50, -1, 49])
+    with pytest.raises(IndexError):
+        fits_dict.fits_get(store, idx, torch.zeros(4), torch.zeros(4, dtype=torch.uint8))
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    pose, betas = fits_dict.fits_get(store, idx, torch.zeros(4), torch.zeros(4, dtype=torch.uint8), status=flag)
+    assert int(flag.item()) == 1
+    assert torch.isnan(pose[1:3]).all() and torch.isnan(betas[1:3]).all()
+    np.testing.assert_allclose(betas[[0, 3]].cpu().numpy(), arr[[3, 49], 72:], rtol=0, atol=0)
+    flag.zero_()
+    fits_dict.fits_set(store, idx, torch.zeros(4), torch.zeros(4, dtype=torch.uint8), torch.ones(4, dtype=torch.uint8),
+                       torch.zeros(4, 72).cuda(), torch.ones(4, 10).cuda(), status=flag)
+    assert int(flag.item()) == 1
+    after = store.cpu().numpy()
+    assert np.array_equal(after[[i for i in range(50) if i not in (3, 49)]], arr[[i for i in range(50) if i not in (3, 49)]])
+    assert np.all(after[[3, 49], 72:] == 1)
+    # the class: an index beyond ITS dataset (but inside the shared store) is caught too
+    fd = fits_dict.FitsDict(type('O', (), {'checkpoint_dir': str(tmp_path)})(), None, fits={'a': arr, 'b': arr[:20].copy()})
+    p, b = fd[(['a', 'b', 'b'], torch.tensor([49, 19, 20]), torch.zeros(3), torch.zeros(3, dtype=torch.uint8))]
+    assert torch.isnan(p[2]).all() and not torch.isnan(p[:2]).any()
+    with pytest.raises(IndexError):
+        fd.check()
+    fd.check()                                                             # the flag is cleared by the raise
+    assert fd.fits_dict['b'].shape == (20, 82) and fd.fits_dict['b'].data_ptr() == fd._store[50:].data_ptr()
+
+
 def test_keep_better():
     gen = torch.Generator().manual_seed(9)
     B = 777

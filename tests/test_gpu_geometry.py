@@ -42,3 +42,46 @@ def test_projection_forward_backward():
     f = torch.full((8,), 5000.).cuda()
     pr2 = geometry.perspective_projection(pts.detach(), rot.detach(), tr.detach(), f, cen)
     assert torch.equal(pr2, pr.detach())
+
+
+@pytest.mark.parametrize('tag', ['verts', 'joints'])
+def test_projection_out_3d_forward_backward(tag):
+    """utils/geometry.py:108-114 (out_3d=True; train/trainer.py:621-626 calls it on the 6890 vertices): third channel = depth."""
+    g = golden('geometry_out3d.npz')
+    pts = torch.from_numpy(g[tag + '_points']).cuda().requires_grad_(True)
+    rot = torch.from_numpy(g[tag + '_rotation']).cuda().requires_grad_(True)
+    tr = torch.from_numpy(g[tag + '_translation']).cuda().requires_grad_(True)
+    cen = torch.from_numpy(g[tag + '_center']).cuda()
+    pr = geometry.perspective_projection(pts, rot, tr, 5000., cen, out_3d=True)
+    assert pr.shape == g[tag + '_projected'].shape and pr.shape[-1] == 3
+    np.testing.assert_allclose(pr.detach().cpu().numpy(), g[tag + '_projected'], rtol=2e-6, atol=2e-4)
+    # the first two channels are the 2-D projection, bit for bit
+    assert torch.equal(pr.detach()[..., :2], geometry.perspective_projection(pts.detach(), rot.detach(), tr.detach(), 5000., cen))
+    (pr * torch.from_numpy(g[tag + '_grad_projected']).cuda()).sum().backward()
+    np.testing.assert_allclose(pts.grad.cpu().numpy(), g[tag + '_grad_points'], rtol=1e-4, atol=1e-3)
+    sc = np.abs(g[tag + '_grad_rotation']).max()
+    np.testing.assert_allclose(rot.grad.cpu().numpy(), g[tag + '_grad_rotation'], rtol=1e-4, atol=1e-5 * sc)
+    sc = np.abs(g[tag + '_grad_translation']).max()
+    np.testing.assert_allclose(tr.grad.cpu().numpy(), g[tag + '_grad_translation'], rtol=1e-4, atol=1e-5 * sc)
+
+
+def test_projection_broadcast_rotation_and_rejected_grads():
+    """A rotation given as [3,3] / [1,3,3] (the reference's einsum broadcasts it) gets the gradient summed over the batch;
+    intrinsics that require grad are refused rather than silently ignored."""
+    g = golden('geometry.npz')
+    pts = torch.from_numpy(g['points']).cuda()
+    tr = torch.from_numpy(g['translation']).cuda()
+    cen = torch.from_numpy(g['center']).cuda()
+    gp = torch.from_numpy(g['grad_projected']).cuda()
+    R0 = torch.from_numpy(g['rotation'][0]).cuda()
+    full = R0[None].expand(8, 3, 3).contiguous().requires_grad_(True)
+    (geometry.perspective_projection(pts, full, tr, 5000., cen) * gp).sum().backward()
+    for shape in ((3, 3), (1, 3, 3)):
+        r = R0.reshape(shape).clone().requires_grad_(True)
+        (geometry.perspective_projection(pts, r, tr, 5000., cen) * gp).sum().backward()
+        assert r.grad.shape == shape
+        np.testing.assert_allclose(r.grad.reshape(3, 3).cpu().numpy(), full.grad.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    with pytest.raises(NotImplementedError):
+        geometry.perspective_projection(pts, full, tr, torch.full((8,), 5000., device='cuda', requires_grad=True), cen)
+    with pytest.raises(NotImplementedError):
+        geometry.perspective_projection(pts, full, tr, 5000., cen.clone().requires_grad_(True))

@@ -87,6 +87,19 @@ def test_joints_only_grad_and_no_grad(smpl, oracle64):
     o = oracle64(global_orient=p64[:, :3], body_pose=p64[:, 3:], betas=torch.tensor(inp['betas'], dtype=torch.float64))
     o.joints.square().sum().backward()
     np.testing.assert_allclose(pose.grad.cpu().numpy(), p64.grad.numpy(), rtol=1e-4, atol=1e-4)
+    # a joints-only loss must not run the tcgen05 vertex backward on a zero gradient: one launch (the pose backward kernel)
+    from inbed_pose_estimation_b200 import _native
+    p2 = torch.from_numpy(inp['pose']).cuda().requires_grad_(True)
+    out = smpl(global_orient=p2[:, :3], body_pose=p2[:, 3:], betas=betas)
+    loss = out.joints.square().sum()
+    _native.lib().smplb200_launch_count(1)
+    loss.backward()
+    assert _native.lib().smplb200_launch_count(0) == 1
+    assert torch.equal(p2.grad, pose.grad)
+    # neither output used: zero gradient, no launch at all
+    p3 = torch.from_numpy(inp['pose']).cuda().requires_grad_(True)
+    out = smpl(global_orient=p3[:, :3], body_pose=p3[:, 3:], betas=betas)
+    (out.joints.sum() * 0 + p3.sum()).backward()
     with torch.no_grad():
         out = smpl(global_orient=pose[:, :3], body_pose=pose[:, 3:], betas=betas)
     assert not out.vertices.requires_grad

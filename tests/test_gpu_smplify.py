@@ -52,7 +52,7 @@ def test_fit_matches_oracle_batch32(fitter, oracle_fp32):
     tr = fitter.last_loss_trace.cpu().numpy()
     tr_o = torch.stack(trace_o).numpy()
     np.testing.assert_allclose(tr.astype(np.float64).sum(1), tr_o.astype(np.float64).sum(1), rtol=1e-5)
-    np.testing.assert_allclose(tr, tr_o, rtol=5e-5)                  # per sample
+    np.testing.assert_allclose(tr, tr_o, rtol=1e-5)                  # per sample, every iteration (north_star: 1e-5 relative)
     np.testing.assert_allclose(pose.cpu().numpy(), po.numpy(), atol=1e-4)
     np.testing.assert_allclose(betas.cpu().numpy(), bo.numpy(), atol=1e-4)
     np.testing.assert_allclose(cam.cpu().numpy(), co.detach().numpy(), atol=1e-4)
