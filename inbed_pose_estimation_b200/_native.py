@@ -171,7 +171,7 @@ def _declare(lib):
         getattr(lib, name).restype = sz
         getattr(lib, name).argtypes = [ci]
     lib.smplb200_smplify_fit.restype = ci
-    lib.smplb200_smplify_fit.argtypes = [vp, ci, ci, cd, cf] + [vp] * 12 + [vp, sz, vp]
+    lib.smplb200_smplify_fit.argtypes = [vp, ci, ci, cd, cf] + [vp] * 13 + [vp, sz, vp]
     lib.smplb200_smplify_fitting_loss.restype = ci
     lib.smplb200_smplify_fitting_loss.argtypes = [vp, ci, cf] + [vp] * 6 + [vp, sz, vp]
     lib.smplb200_prior_terms.restype = ci
@@ -190,6 +190,8 @@ def _declare(lib):
     lib.smplb200_perspective_projection_backward.argtypes = [ci, ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp]
     lib.smplb200_probe_fp32_peak.restype = ci
     lib.smplb200_probe_fp32_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.smplb200_probe_tf32_peak.restype = ci
+    lib.smplb200_probe_tf32_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
     lib.smplb200_rot6d_to_rotmat.restype = ci
     lib.smplb200_rot6d_to_rotmat.argtypes = [ci, vp, vp, vp]
     lib.smplb200_rotmat_to_axis_angle.restype = ci
@@ -235,7 +237,7 @@ EXPORTED_SYMBOLS = (
     'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
     'smplb200_fit_tile_plan', 'smplb200_weak_perspective_projection', 'smplb200_weak_perspective_projection_backward',
     'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
-    'smplb200_prior_terms',
+    'smplb200_prior_terms', 'smplb200_probe_tf32_peak',
 )
 
 

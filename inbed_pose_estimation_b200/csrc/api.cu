@@ -225,7 +225,7 @@ static AdamConsts adam_consts(double beta1, double beta2) {
 static int run_fit(const smplb200_model* m, int batch, int num_iters, double step_size, float focal, int loss_only,
                    const float* pose, const float* betas, const float* cam, const float* center, float* kp,
                    float* vertices, float* joints, float* opose, float* obetas, float* ocam, float* reproj, float* trace,
-                   void* ws, size_t ws_bytes, cudaStream_t st, cudaEvent_t after_fit = nullptr) {
+                   void* ws, size_t ws_bytes, cudaStream_t st, cudaEvent_t after_fit = nullptr, float* packed = nullptr) {
     if (!m) return fail("NULL model");
     if (batch < 0) return fail("negative batch");
     if (batch == 0) return 0;
@@ -242,6 +242,7 @@ static int run_fit(const smplb200_model* m, int batch, int num_iters, double ste
     P.focal = focal;
     P.init_pose = pose; P.init_betas = betas; P.init_cam = cam; P.center = center; P.keypoints = kp;
     P.out_joints = joints; P.out_pose = opose; P.out_betas = obetas; P.out_cam = ocam; P.out_reproj = reproj;
+    P.out_packed = packed;
     if (vertices) P.tc = wk.tc;
     P.loss_trace = trace;
     P.lr = step_size; P.beta1 = 0.9; P.beta2 = 0.999;        // lr stays a double: torch divides the Python float by bc1
@@ -257,11 +258,11 @@ extern "C" int smplb200_smplify_fit(const smplb200_model* model, int batch, int 
                                     const float* init_pose, const float* init_betas, const float* init_cam_t,
                                     const float* camera_center, float* keypoints_2d, float* vertices, float* joints,
                                     float* pose, float* betas, float* camera_translation, float* reprojection_loss,
-                                    float* loss_trace, void* workspace, size_t workspace_bytes, void* stream) {
+                                    float* loss_trace, float* packed_results, void* workspace, size_t workspace_bytes, void* stream) {
     if (!joints || !pose || !betas || !camera_translation) return fail("smplify_fit: NULL output buffer");
     return run_fit(model, batch, num_iters, step_size, focal_length, 0, init_pose, init_betas, init_cam_t, camera_center,
                    keypoints_2d, vertices, joints, pose, betas, camera_translation, reprojection_loss, loss_trace, workspace,
-                   workspace_bytes, static_cast<cudaStream_t>(stream));
+                   workspace_bytes, static_cast<cudaStream_t>(stream), nullptr, packed_results);
 }
 
 extern "C" int smplb200_smplify_fitting_loss(const smplb200_model* model, int batch, float focal_length, const float* pose,

@@ -37,6 +37,7 @@ struct FitParams {
     float* out_betas;         // [B][10]     (nullable)
     float* out_cam;           // [B][3]      (nullable)
     float* out_reproj;        // [B][49]
+    float* out_packed;        // [B][134] (nullable) pose 72 | betas 10 | camera 3 | reprojection 49: the row a sharded refit gathers
     TcOperands tc;            // (nullable members) hi/lo tf32 operands of the tcgen05 vertex kernels for the final pose
     float* loss_trace;        // [2*num_iters][B] (nullable) per-sample loss of every iteration
     double lr, beta1, beta2;  // Adam hyper-parameters (smplify.py:79,107: lr=step_size, betas=(0.9, 0.999))
@@ -377,6 +378,19 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
     FOR_ITEMS(it, S * 3) {
         const int s = it / 3, k = it % 3, b = first + s;
         if (P.out_cam && b < P.batch) P.out_cam[(size_t)b * 3 + k] = sm[L::CAM + k * S + s];
+    }
+    if (P.out_packed) {
+        constexpr int kPacked = 72 + kBetas + 3 + kOut;
+        FOR_ITEMS(it, S * kPacked) {
+            const int s = it / kPacked, k = it % kPacked, b = first + s;
+            if (b >= P.batch) continue;
+            float v;
+            if (k < 72) v = sm[L::POSE + k * S + s];
+            else if (k < 72 + kBetas) v = sm[L::BETA + (k - 72) * S + s];
+            else if (k < 72 + kBetas + 3) v = sm[L::CAM + (k - 72 - kBetas) * S + s];
+            else v = sm[L::LOSSJ + (k - 72 - kBetas - 3) * S + s];
+            P.out_packed[(size_t)b * kPacked + k] = v;
+        }
     }
 }
 

@@ -2,6 +2,7 @@
 // (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers).  Scalar FFMA and Blackwell packed FFMA2.
 #include <cuda_runtime.h>
 #include "../../include/smplify_b200.h"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -74,6 +75,75 @@ extern "C" int smplb200_probe_fp32_peak(int packed, double* tflops) {
     cudaFree(out);
     if (e != cudaSuccess || ms <= 0.f) return 1;
     const double flops = 2.0 * 2 * (packed ? 2 : 1) * N * (double)iters * blocks * threads * reps;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+// tcgen05 kind::tf32 peak probe: one warp per SM issues back-to-back M=128 N=256 K=8 MMAs (operands in shared memory, one
+// fp32 accumulator tile in TMEM; the operand values do not matter for the rate).  This is the tensor-pipe denominator of the
+// 3xTF32 LBS kernels - MEASURED_PEAKS.json only has the bf16 figure.
+namespace {
+using namespace smplb200::tc;
+constexpr int kTf32ProbeMmas = 8192;
+
+__global__ void __launch_bounds__(64, 1) probe_tf32_kernel(int* sink) {
+    extern __shared__ float probe_smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    float* smem = probe_smem_raw + ((1024u - (smem_u32(probe_smem_raw) & 1023u)) & 1023u) / 4;
+    for (int i = threadIdx.x; i < (16 + 32) * 256; i += 64) smem[i] = 0.f;          // A tile 16 KB, B tile 32 KB
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc<256>(smem_u32(&slot));
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    if (threadIdx.x < 32) {
+        const uint64_t da = smem_desc(smem_u32(smem)), db = smem_desc(smem_u32(smem) + 16384);
+        constexpr uint32_t idesc = instr_desc(128, 256);
+        if (elect_one()) {
+#pragma unroll 8
+            for (int r = 0; r < kTf32ProbeMmas; ++r)
+                umma_tf32(tm, da + (uint64_t)(2 * (r & 3)), db + (uint64_t)(2 * (r & 3)), idesc, r ? 1u : 0u);
+            umma_commit(smem_u32(&bar));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&bar), 0);
+        tc_fence_after();
+        if (threadIdx.x == 0 && sink) sink[blockIdx.x] = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<256>(tm); }
+}
+}  // namespace
+
+extern "C" int smplb200_probe_tf32_peak(double* tflops) {
+    if (!tflops) return 1;
+    cudaDeviceProp p;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess || p.major < 10) return 1;
+    const int smem_bytes = 49 * 1024 + 1024, blocks = p.multiProcessorCount;
+    if (cudaFuncSetAttribute(probe_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return 1;
+    int* sink = nullptr;
+    if (cudaMalloc(&sink, sizeof(int) * blocks) != cudaSuccess) return 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) probe_tf32_kernel<<<blocks, 64, smem_bytes>>>(sink);
+    cudaEventRecord(e0);
+    const int reps = 5;
+    for (int i = 0; i < reps; ++i) probe_tf32_kernel<<<blocks, 64, smem_bytes>>>(sink);
+    cudaEventRecord(e1);
+    const cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess || ms <= 0.f) return 1;
+    const double flops = 2.0 * 128 * 256 * 8 * (double)kTf32ProbeMmas * blocks * reps;
     *tflops = flops / (ms * 1e-3) / 1e12;
     return 0;
 }

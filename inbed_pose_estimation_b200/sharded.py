@@ -24,13 +24,18 @@ def unpack_results(packed):
 
 
 def gather_rows(local, n_total, group=None):
-    """All-gather a [n_local, C] tensor whose row counts follow shard_bounds -> [n_total, C] on every rank."""
+    """All-gather a [n_local, C] tensor whose row counts follow shard_bounds -> [n_total, C] on every rank.
+    When the rows divide evenly over the ranks the local tensor is gathered as it is (no padded copy)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
     rank = dist.get_rank(group)
     sizes = [shard_bounds(n_total, world, r) for r in range(world)]
     max_rows = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == max_rows for lo, hi in sizes) and local.is_contiguous():
+        out = local.new_empty((n_total, local.shape[1]))
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
     padded = local.new_zeros((max_rows, local.shape[1]))
     padded[:local.shape[0]] = local
     out = local.new_empty((world * max_rows, local.shape[1]))
@@ -83,6 +88,7 @@ class ShardedRefit(object):
 
     def __init__(self, smplify=None, fit_fn=None, group=None, device=None):
         self.fit_fn = fit_fn if fit_fn is not None else smplify
+        self._packs = fit_fn is None and smplify is not None        # the CUDA SMPLify writes the packed rows itself
         self.group = group
         self.device = device if device is not None else (smplify.device if smplify is not None else None)
 
@@ -93,9 +99,13 @@ class ShardedRefit(object):
         lo, hi = shard_bounds(n, world, rank)
         dev = self.device if self.device is not None else fits.device
         sl = lambda t: t[lo:hi].to(dev, non_blocking=True).contiguous()
-        out = self.fit_fn(sl(fits[:, :72]), sl(fits[:, 72:]), sl(cam_t), sl(center), sl(keypoints).clone())
-        _, _, pose, betas, cam, reproj = out
-        packed = gather_rows(pack_results(pose, betas, cam.detach(), reproj), n, self.group)
+        if self._packs:
+            local = torch.empty((hi - lo, PACKED), device=dev, dtype=torch.float32)
+            self.fit_fn(sl(fits[:, :72]), sl(fits[:, 72:]), sl(cam_t), sl(center), sl(keypoints).clone(), packed_out=local)
+        else:
+            _, _, pose, betas, cam, reproj = self.fit_fn(sl(fits[:, :72]), sl(fits[:, 72:]), sl(cam_t), sl(center), sl(keypoints).clone())
+            local = pack_results(pose, betas, cam.detach(), reproj)
+        packed = gather_rows(local, n, self.group)
         pose, betas, cam, reproj = unpack_results(packed)
         new_loss = reproj.mean(dim=-1)                       # trainer.py:716
         new_fits = torch.cat([pose, betas], dim=1)

@@ -62,9 +62,11 @@ class SMPLify(object):
             return keypoints_2d.detach(), None
         return keypoints_2d.detach().contiguous().float(), keypoints_2d
 
-    def __call__(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, return_loss_trace=False):
+    def __call__(self, init_pose, init_betas, init_cam_t, camera_center, keypoints_2d, return_loss_trace=False, packed_out=None):
         """Perform body fitting.  Returns (vertices [B,6890,3], joints [B,49,3], pose [B,72], betas [B,10],
-        camera_translation [B,3], reprojection_loss [B,49])."""
+        camera_translation [B,3], reprojection_loss [B,49]).  packed_out: optional contiguous fp32 CUDA tensor [B,134] that
+        additionally receives pose | betas | camera | reprojection of every sample as one row, written by the fit kernel itself
+        (the row a sharded refit all-gathers, sharded.PACKED)."""
         B = init_pose.shape[0]
         self._dev = init_pose.device
         pose = self._prep(init_pose, (B, 72), 'init_pose')
@@ -78,6 +80,9 @@ class SMPLify(object):
         o_pose, o_betas, o_cam, reproj = new(B, 72), new(B, 10), new(B, 3), new(B, constants.NUM_JOINTS_OUT)
         trace = new(2 * self.num_iters, B) if return_loss_trace else None
         self.last_loss_trace = trace
+        if packed_out is not None and not (packed_out.is_cuda and packed_out.is_contiguous() and packed_out.dtype == torch.float32
+                                           and tuple(packed_out.shape) == (B, 134)):
+            raise ValueError('packed_out must be a contiguous fp32 CUDA tensor [B, 134]')
         if B == 0:
             return vertices, joints, o_pose, o_betas, o_cam, reproj
         ws = self._workspace(B)
@@ -86,7 +91,7 @@ class SMPLify(object):
                 self.smpl.native(dev).handle, B, int(self.num_iters), float(self.step_size), float(self.focal_length),
                 _native.ptr(pose), _native.ptr(betas), _native.ptr(cam), _native.ptr(cen), _native.ptr(kp),
                 _native.ptr(vertices), _native.ptr(joints), _native.ptr(o_pose), _native.ptr(o_betas), _native.ptr(o_cam),
-                _native.ptr(reproj), _native.ptr(trace), ws.data_ptr(), ws.numel(),
+                _native.ptr(reproj), _native.ptr(trace), _native.ptr(packed_out), ws.data_ptr(), ws.numel(),
                 torch.cuda.current_stream(dev).cuda_stream))
         if writeback is not None:
             writeback[:, self.ign_joints, 2] = 0.

@@ -78,7 +78,9 @@ size_t smplb200_smpl_workspace_bytes(int batch);
 
 /* SMPLify.__call__ (smplify/smplify.py:40-136): two-stage fit, num_iters Adam steps per stage.
  * keypoints [B][49][3] is read AND its confidences at ign_joints are zeroed in place after the
- * camera stage, exactly like the reference (:105).  vertices / loss_trace may be NULL.
+ * camera stage, exactly like the reference (:105).  vertices / loss_trace / packed_results may be NULL.
+ * packed_results [B][134]: the fitted pose (72), betas (10), camera translation (3) and per-joint reprojection loss (49)
+ * of every sample as one row - the row a sharded refit all-gathers (the kernel writes it besides the separate outputs).
  * loss_trace [2*num_iters][B]: per-sample loss of every iteration (stage 1 then stage 2).
  * step_size is the Adam lr as a double: torch.optim.Adam divides the Python float by the bias
  * correction in float64 before the fp32 cast (smplify.py:79,107), and so does the kernel. */
@@ -89,6 +91,7 @@ int smplb200_smplify_fit(const smplb200_model* model, int batch, int num_iters, 
                          float* vertices /*device [B][6890][3] or NULL*/, float* joints /*device [B][49][3]*/,
                          float* pose /*device [B][72]*/, float* betas /*device [B][10]*/, float* camera_translation /*device [B][3]*/,
                          float* reprojection_loss /*device [B][49]*/, float* loss_trace /*device or NULL*/,
+                         float* packed_results /*device [B][134] or NULL*/,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* SMPLify.get_fitting_loss (smplify/smplify.py:138-172): zeroes the ignored confidences in place
@@ -243,6 +246,11 @@ long long smplb200_launch_count(int reset);
 /* Measures the fp32 FMA rate of the CUDA-core pipes on the current device (packed = 0: scalar FFMA,
  * 1: Blackwell packed FFMA2) - the roofline denominator bench.py uses for the SIMT-bound fit kernel. */
 int smplb200_probe_fp32_peak(int packed, double* tflops);
+
+/* Measures the dense tcgen05 kind::tf32 rate (M=128 N=256 K=8 MMAs issued back to back on every SM, fp32 accumulators in
+ * TMEM) on the current device: the tensor-pipe denominator of the 3xTF32 LBS kernels (one fp32-accurate product costs three
+ * such MMAs). */
+int smplb200_probe_tf32_peak(double* tflops);
 
 #ifdef __cplusplus
 }
