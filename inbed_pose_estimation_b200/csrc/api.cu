@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -33,7 +34,7 @@ struct smplb200_model {
 };
 
 static thread_local std::string g_error;
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};      // process-wide: autograd runs backward calls on its own threads
 
 static int fail(const char* fmt, ...) {
     char buf[512];
@@ -88,9 +89,7 @@ extern "C" int smplb200_debug_phase_clocks(unsigned long long* out32, int reset)
 #endif
 
 extern "C" long long smplb200_launch_count(int reset) {
-    const long long v = g_launches;
-    if (reset) g_launches = 0;
-    return v;
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 template <typename T>

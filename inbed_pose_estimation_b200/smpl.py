@@ -58,6 +58,8 @@ class _SMPLFunction(torch.autograd.Function):
     def forward(ctx, module, pose, betas, rotmat_mode, need_vertices):
         B = betas.shape[0]
         dev = betas.device
+        if dev.type != 'cuda':
+            module.native(dev)                       # raises: CUDA only, no CPU fallback
         lib = _native.lib()
         pose_c = pose.detach().contiguous().float()
         betas_c = betas.detach().contiguous().float()

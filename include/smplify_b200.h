@@ -239,8 +239,8 @@ int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_it
  * samples followed by n_small tiles of `small` (4, 8 or 12; 0 = none) samples.  Pure host arithmetic. */
 void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_small);
 
-/* Number of this library's kernel launches issued by the calling thread since the last reset
- * (bench.py reports it as gpu_launches). */
+/* Number of this library's kernel launches issued by the process (any thread: torch autograd runs backward calls on
+ * its own threads) since the last reset; reset != 0 returns the count and clears it (bench.py reports it as gpu_launches). */
 long long smplb200_launch_count(int reset);
 
 /* Measures the fp32 FMA rate of the CUDA-core pipes on the current device (packed = 0: scalar FFMA,

@@ -49,12 +49,7 @@ def _assert_loss_trace(got, ref32, inp, rows, what, max_adjudicated=4):
     if bad.size == 0:
         return
     assert bad.size <= max_adjudicated, '%s: %d samples beyond 1e-5 (max rel %.2e)' % (what, bad.size, rel.max())
-    from oracle import port
-    if not _O64:
-        _O64.append(port.build_oracle(seed=0, dtype=torch.float64))
-    tr64 = []
-    _O64[0](*[torch.from_numpy(inp[k][rows][bad].copy()).double() for k in KEYS], trace=tr64)
-    tr64 = torch.stack(tr64).numpy()
+    _, tr64 = _oracle64_rows(inp, rows[bad])
     ours = np.abs(got[:, bad] - tr64) / np.abs(tr64)
     theirs = np.abs(ref32[:, bad] - tr64) / np.abs(tr64)
     assert ours.max() <= 1e-5, '%s: %.2e from the float64 oracle' % (what, ours.max())
@@ -62,17 +57,53 @@ def _assert_loss_trace(got, ref32, inp, rows, what, max_adjudicated=4):
     assert np.all(theirs[off] > ours[off]), what + ': the deviation is not the fp32 oracle\'s own rounding'
 
 
-def _assert_fit_rows(out, trace, rows, ref, ref_trace, what, inp=None):
-    """out: the six result tensors of the big GPU fit; trace [200, B]; rows: the row indices the oracle fitted."""
-    v, j, pose, betas, cam, reproj = [t[rows].cpu().numpy() for t in out]
-    vo, jo, po, bo, co, ro = [t.detach().numpy() for t in ref]
+def _oracle64_rows(inp, rows):
+    from oracle import port
+    if not _O64:
+        _O64.append(port.build_oracle(seed=0, dtype=torch.float64))
+    tr64 = []
+    out = _O64[0](*[torch.from_numpy(inp[k][rows].copy()).double() for k in KEYS], trace=tr64)
+    return [t.detach().numpy() for t in out], torch.stack(tr64).numpy()
+
+
+def _assert_fit_rows(out, trace, rows, ref, ref_trace, what, inp=None, max_adjudicated=4):
+    """out: the six result tensors of the big GPU fit; trace [200, B]; rows: the row indices the oracle fitted.
+
+    Fitted parameters / joints / vertices: 1e-4 absolute against the fp32 oracle.  A fit is 200 chained Adam steps and a few
+    samples are ill-conditioned enough that the fp32 ORACLE ITSELF ends more than 1e-4 away from the same oracle run in
+    float64 (build container, batch 256, seed 33: rows 246 and 249, 1.5e-4 and 2.3e-4; this library 1.3e-5 and 1.2e-4 from
+    float64 on the same rows).  Rows beyond 1e-4 are therefore adjudicated in float64: this library must be no farther from
+    the float64 result than max(1e-4, twice the fp32 oracle's own distance to it)."""
+    got = [t[rows].cpu().numpy() for t in out]
+    want = [t.detach().numpy() for t in ref]
     _assert_loss_trace(trace[:, rows], ref_trace, inp, rows, what + ': per-sample loss of every iteration')
-    np.testing.assert_allclose(pose, po, atol=1e-4, err_msg=what)
-    np.testing.assert_allclose(betas, bo, atol=1e-4, err_msg=what)
-    np.testing.assert_allclose(cam, co, atol=1e-4, err_msg=what)
-    np.testing.assert_allclose(j, jo, atol=1e-4, err_msg=what)
-    np.testing.assert_allclose(v, vo, atol=1e-4, err_msg=what)
-    np.testing.assert_allclose(reproj, ro, rtol=1e-4, atol=1e-2, err_msg=what)
+    good = _adjudicated_close(got[:5], want[:5], ('vertices', 'joints', 'pose', 'betas', 'camera'), (0, 1, 2, 3, 4), inp, rows, what,
+                              max_adjudicated)
+    np.testing.assert_allclose(got[5][good], want[5][good], rtol=1e-4, atol=1e-2, err_msg=what + ': reprojection')
+
+
+def _adjudicated_close(got, want, names, oracle_slots, inp, rows, what, max_adjudicated=4):
+    """got / want: lists of [len(rows), ...] arrays (this library / the fp32 oracle); oracle_slots: which entries of the oracle's
+    6-tuple they are.  1e-4 absolute; rows beyond it are re-fitted by the float64 oracle and must be no farther from it than
+    max(1e-4, twice the fp32 oracle's own distance).  Returns the indices of the rows that met 1e-4 directly."""
+    bad = set()
+    for g, w in zip(got, want):
+        err = np.abs(g - w).reshape(len(rows), -1).max(axis=1)
+        bad.update(np.nonzero(err > 1e-4)[0].tolist())
+    bad = sorted(bad)
+    assert len(bad) <= max_adjudicated, '%s: %d rows beyond 1e-4 of the fp32 oracle' % (what, len(bad))
+    good = np.setdiff1d(np.arange(len(rows)), bad)
+    for g, w, nm in zip(got, want, names):
+        np.testing.assert_allclose(g[good], w[good], atol=1e-4, err_msg='%s: %s' % (what, nm))
+    if bad:
+        ref64, _ = _oracle64_rows(inp, np.asarray(rows)[bad])
+        for g, w, slot, nm in zip(got, want, oracle_slots, names):
+            x = ref64[slot]
+            ours = np.abs(g[bad] - x).reshape(len(bad), -1).max(axis=1)
+            theirs = np.abs(w[bad] - x).reshape(len(bad), -1).max(axis=1)
+            assert np.all(ours <= np.maximum(1e-4, 2.0 * theirs)), \
+                '%s: %s rows %s: %s from the float64 oracle (the fp32 oracle: %s)' % (what, nm, np.asarray(rows)[bad], ours, theirs)
+    return good
 
 
 def test_headline_batch_rows_match_oracle(fitter, oracle_fp32):
@@ -138,10 +169,10 @@ def test_bulk_refit_shards_match_oracle(fitter, oracle_fp32):
         assert np.array_equal(up1[rows].cpu().numpy()[margin], better[margin])
         sel = better & margin
         assert sel.sum() >= 16
-        np.testing.assert_allclose(f1[rows][:, :72].cpu().numpy()[sel], ref[2].numpy()[sel], atol=1e-4)
-        np.testing.assert_allclose(f1[rows][:, 72:].cpu().numpy()[sel], ref[3].numpy()[sel], atol=1e-4)
-        np.testing.assert_allclose(cam1[rows].cpu().numpy()[sel], ref[4].detach().numpy()[sel], atol=1e-4)
-        np.testing.assert_allclose(l1[rows].cpu().numpy()[sel], new_loss[sel], rtol=1e-4)
+        good = _adjudicated_close([f1[rows][:, :72].cpu().numpy()[sel], f1[rows][:, 72:].cpu().numpy()[sel], cam1[rows].cpu().numpy()[sel]],
+                                  [ref[2].numpy()[sel], ref[3].numpy()[sel], ref[4].detach().numpy()[sel]], ('pose', 'betas', 'camera'),
+                                  (2, 3, 4), inp, rows[sel], 'bulk refit shard')
+        np.testing.assert_allclose(l1[rows].cpu().numpy()[sel][good], new_loss[sel][good], rtol=1e-4)
 
 
 # ---- priors in isolation ---------------------------------------------------------------------------------------------
