@@ -63,11 +63,11 @@ constexpr float kDepthW2 = 100.f * 100.f;             // depth_loss_weight ** 2 
 
 // Stage the small constants in shared memory (device) or just point at them (host emulation).
 // The caller must place a barrier before the first use.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD SmallConsts stage_small_consts(const ModelView& M, float* sm) {
     SmallConsts C;
 #if defined(__CUDA_ARCH__)
-    float* b = sm + TileLayout<S>::CONSTS;
+    float* b = sm + L::CONSTS;
     float* JS = b; float* J0 = JS + 720; float* wkj = J0 + 72; float* Wp = wkj + 216;
     float* mu = Wp + 264; float* pmean = mu + 576; float* lognll = pmean + 576;
     FOR_ITEMS(i, 720) JS[i] = M.JS[i];
@@ -87,60 +87,59 @@ SB_HD SmallConsts stage_small_consts(const ModelView& M, float* sm) {
 // Kinematic chain + folded forward GEMM (independent of each other: the chain reads the rotations and rest joints, the
 // GEMM reads x).  On the device with the standard 384-thread tile the chain's level sweeps run on warp 11, which no GEMM
 // work item lands on, concurrently with the GEMM; otherwise one after the other.  Ends with a tile barrier.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_chain_and_gemm_forward(const ModelView& M, float* sm) {
 #if defined(__CUDA_ARCH__)
     if (kFastGemm<S> && TILE_NT == kFitTileThreads) {
-        if (TILE_TID >= kChainWarpFirstThread) ph_chain_forward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
-        else ph_fold_gemm_forward<S>(M, sm);
+        if (TILE_TID >= kChainWarpFirstThread) ph_chain_forward<S, L>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
+        else ph_fold_gemm_forward<S, L>(M, sm);
         TILE_SYNC();
         return;
     }
 #endif
-    ph_chain_forward<S>(M, sm, grp_tile());           // ends with a barrier
-    ph_fold_gemm_forward<S>(M, sm);
+    ph_chain_forward<S, L>(M, sm, grp_tile());           // ends with a barrier
+    ph_fold_gemm_forward<S, L>(M, sm);
     TILE_SYNC();
 }
 
 // Folded backward GEMM + reverse chain sweep, overlapped the same way (the sweep needs dL/dG from ph_joint_backward only;
 // the GEMM's dL/dx is added to dL/dR afterwards in rotation_grad).  Ends with a tile barrier.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_gemm_and_chain_backward(const ModelView& M, float* sm) {
 #if defined(__CUDA_ARCH__)
     if (kFastGemm<S> && TILE_NT == kFitTileThreads) {
-        if (TILE_TID >= kChainWarpFirstThread) ph_chain_backward<S>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
-        ph_fold_gemm_backward<S>(M, sm);              // warp 11 owns no GEMM range: it only joins the barriers and the combine
+        if (TILE_TID >= kChainWarpFirstThread) ph_chain_backward<S, L>(M, sm, Grp{TILE_TID - kChainWarpFirstThread, 32, 1});
+        ph_fold_gemm_backward<S, L>(M, sm);              // warp 11 owns no GEMM range: it only joins the barriers and the combine
         TILE_SYNC();
         return;
     }
 #endif
-    ph_fold_gemm_backward<S>(M, sm);
+    ph_fold_gemm_backward<S, L>(M, sm);
     TILE_SYNC();
-    ph_chain_backward<S>(M, sm, grp_tile());
+    ph_chain_backward<S, L>(M, sm, grp_tile());
     TILE_SYNC();
 }
 
 // forward through the folded joint model for the tile's current parameters
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void tile_forward(const ModelView& M, const SmallConsts& C, float* sm, bool from_axis_angle, bool root_identity) {
-    ph_pose_features<S>(sm, from_axis_angle, root_identity);
-    ph_rest_joints<S>(C, sm);
+    ph_pose_features<S, L>(sm, from_axis_angle, root_identity);
+    ph_rest_joints<S, L>(C, sm);
     TILE_SYNC();
-    ph_chain_and_gemm_forward<S>(M, sm);
-    ph_output_joints<S>(M, C, sm);
+    ph_chain_and_gemm_forward<S, L>(M, sm);
+    ph_output_joints<S, L>(M, C, sm);
     TILE_SYNC();
 }
 
 // Skinning transforms A = [G^R | A^t] and blend coefficients x of the tile's current pose, written as the hi/lo tf32
 // split operands of the tcgen05 vertex kernels (lbs_tc.cu): x [B][224], transforms [B][12 entries][24 joints + 8 pad].
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void tile_write_vertex_operands(float* sm, int first, int batch, const TcOperands& tc) {
-    using L = TileLayout<S>;
     if (tc.x_hi) {
         FOR_ITEMS(it, S * kXPad) {
             const int s = it / kXPad, k = it % kXPad, b = first + s;
             if (b >= batch) continue;
-            const float x = sm[L::XT + k * S + s];
+            const float x = sm[L::x(k, s)];
             const float hi = tf32_round(x);
             tc.x_hi[(size_t)b * kXPad + k] = hi;
             tc.x_lo[(size_t)b * kXPad + k] = x - hi;
@@ -163,9 +162,8 @@ SB_HD void tile_write_vertex_operands(float* sm, int first, int batch, const TcO
 // Stage 1 (camera_fitting_loss, smplify.py:70-91): only the root rotation and the camera move, so all
 // 49 joints are an affine image of the root-identity pose:  joint = R0 (rest - sigma J0) + sigma J0.
 // One thread per sample runs the whole stage in registers.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
     const AdamScalars* adam_tab = reinterpret_cast<const AdamScalars*>(sm + L::ADAMTAB);
     FOR_ITEMS(s, S) {
         const int b = first + s;
@@ -235,9 +233,8 @@ SB_HD void stage1_camera(const ModelView& M, const FitParams& P, int first, floa
     }
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
     FOR_ITEMS(it, M.num_ign * S) {
         const int s = it % S, o = M.ign_joints[it / S], b = first + s;
         sm[L::KP + (3 * o + 2) * S + s] = 0.f;
@@ -245,12 +242,11 @@ SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int fi
     }
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
     // per-iteration Adam scalars, computed in float64 like torch does on the host
     AdamScalars* adam_tab = reinterpret_cast<AdamScalars*>(sm + L::ADAMTAB);
-    const SmallConsts C = stage_small_consts<S>(M, sm);
+    const SmallConsts C = stage_small_consts<S, L>(M, sm);
     FOR_ITEMS(t, (P.num_iters < kMaxIters ? P.num_iters : kMaxIters)) adam_tab[t] = adam_scalars(P, t);
     // ---- load the tile ---------------------------------------------------------------------
     FOR_ITEMS(it, S * 72) {
@@ -274,38 +270,38 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
         sm[L::KP + k * S + s] = (b < P.batch) ? P.keypoints[(size_t)b * 147 + k] : 0.f;
     }
     TILE_SYNC();
-    if (P.zero_conf_first) { tile_zero_ignored_conf<S>(M, P, first, sm); TILE_SYNC(); }
+    if (P.zero_conf_first) { tile_zero_ignored_conf<S, L>(M, P, first, sm); TILE_SYNC(); }
 
     if (P.num_iters > 0) {
         // ---- stage 1: global orientation + camera translation --------------------------------
-        tile_forward<S>(M, C, sm, true, /*root_identity=*/true);
-        stage1_camera<S>(M, P, first, sm);
+        tile_forward<S, L>(M, C, sm, true, /*root_identity=*/true);
+        stage1_camera<S, L>(M, P, first, sm);
         TILE_SYNC();
-        tile_zero_ignored_conf<S>(M, P, first, sm);
-        zero_rows<S>(sm, L::ADM, 2 * kParams);
+        tile_zero_ignored_conf<S, L>(M, P, first, sm);
+        zero_rows<S, L>(sm, L::ADM, 2 * kParams);
         TILE_SYNC();
 
         // ---- stage 2: body pose, betas, global orientation (body_fitting_loss) ----------------
         PHASE_BEGIN();
         for (int it = 0; it < P.num_iters; ++it) {
-            ph_prior_quadratic<S>(M, C, sm);
+            ph_prior_quadratic<S, L>(M, C, sm);
             TILE_SYNC();
             PHASE_MARK(0);
-            ph_prior_select<S>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
+            ph_prior_select<S, L>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
             TILE_SYNC();
             PHASE_MARK(1);
-            ph_pose_features<S>(sm, true, false);
-            ph_rest_joints<S>(C, sm);
+            ph_pose_features<S, L>(sm, true, false);
+            ph_rest_joints<S, L>(C, sm);
             TILE_SYNC();
             PHASE_MARK(2);
             PHASE_MARK(3);
-            ph_chain_and_gemm_forward<S>(M, sm);
+            ph_chain_and_gemm_forward<S, L>(M, sm);
             PHASE_MARK(4);
-            ph_output_joints<S>(M, C, sm);
+            ph_output_joints<S, L>(M, C, sm);
             TILE_SYNC();
             PHASE_MARK(5);
-            ph_reprojection<S>(sm, P.focal, kSigma2, true);
-            zero_rows<S>(sm, L::DG, 288);
+            ph_reprojection<S, L>(sm, P.focal, kSigma2, true);
+            zero_rows<S, L>(sm, L::DG, 288);
             TILE_SYNC();
             if (P.loss_trace) {
                 FOR_ITEMS(s, S) {
@@ -317,20 +313,20 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
                 }
             }
             PHASE_MARK(6);
-            ph_joint_backward<S>(M, C, sm);
+            ph_joint_backward<S, L>(M, C, sm);
             TILE_SYNC();
             PHASE_MARK(7);
-            ph_pick_backward<S>(M, C, sm);
+            ph_pick_backward<S, L>(M, C, sm);
             TILE_SYNC();
             PHASE_MARK(8);
             PHASE_MARK(9);
-            ph_gemm_and_chain_backward<S>(M, sm);
+            ph_gemm_and_chain_backward<S, L>(M, sm);
             PHASE_MARK(10);
             const AdamScalars sc = (it < kMaxIters) ? adam_tab[it] : adam_scalars(P, it);
             FOR_ITEMS(itj, kJoints * S) {
                 const int s = itj % S, j = itj / S;
                 float g[9], d[3];
-                rotation_grad<S>(sm, j, s, g);
+                rotation_grad<S, L>(sm, j, s, g);
                 rodrigues_bwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
                               sm[L::POSE + (3 * j + 2) * S + s], g, d);
 #pragma unroll
@@ -344,7 +340,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
             FOR_ITEMS(itb, kBetas * S) {
                 const int s = itb % S, l = itb / S;
                 const float beta = sm[L::BETA + l * S + s];
-                const float g = beta_grad<S>(C, sm, l, s) + 2.f * kShapePriorW2 * beta;
+                const float g = beta_grad<S, L>(C, sm, l, s) + 2.f * kShapePriorW2 * beta;
                 sm[L::BETA + l * S + s] = adam_update(beta, g, sm[L::ADM + (72 + l) * S + s], sm[L::ADV + (72 + l) * S + s],
                                                       P.adam_c, sc);
             }
@@ -354,14 +350,14 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
     }
 
     // ---- final forward: joints, per-joint reprojection loss, A and x for the vertex kernel --------
-    tile_forward<S>(M, C, sm, true, false);
+    tile_forward<S, L>(M, C, sm, true, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = first + s;
         if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, first, P.batch, P.tc);
+    tile_write_vertex_operands<S, L>(sm, first, P.batch, P.tc);
     TILE_SYNC();
-    ph_reprojection<S>(sm, P.focal, kSigma2, false);
+    ph_reprojection<S, L>(sm, P.focal, kSigma2, false);
     TILE_SYNC();
     FOR_ITEMS(it, S * kOut) {
         const int s = it / kOut, o = it % kOut, b = first + s;
@@ -410,10 +406,9 @@ struct PriorParams {
     float* grad_betas;        // [B][10] (nullable)
 };
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void prior_tile(const ModelView& M, const PriorParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
-    const SmallConsts C = stage_small_consts<S>(M, sm);
+    const SmallConsts C = stage_small_consts<S, L>(M, sm);
     FOR_ITEMS(it, S * 72) {
         const int s = it / 72, k = it % 72, b = first + s;
         sm[L::POSE + k * S + s] = (b < P.batch) ? P.pose[(size_t)b * 72 + k] : 0.f;
@@ -423,9 +418,9 @@ SB_HD void prior_tile(const ModelView& M, const PriorParams& P, int first, float
         sm[L::BETA + k * S + s] = (b < P.batch) ? P.betas[(size_t)b * kBetas + k] : 0.f;
     }
     TILE_SYNC();
-    ph_prior_quadratic<S>(M, C, sm);
+    ph_prior_quadratic<S, L>(M, C, sm);
     TILE_SYNC();
-    ph_prior_select<S>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
+    ph_prior_select<S, L>(M, C, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
     TILE_SYNC();
     FOR_ITEMS(it, S * 3) {
         const int s = it / 3, k = it % 3, b = first + s;
@@ -484,9 +479,8 @@ SB_HD float4 sum_partials4(const float* p, size_t stride, int n) {
     return a;
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void pose_load(const PoseParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
     if (P.rotmat_mode) {
         FOR_ITEMS(it, S * 216) {
             const int s = it / 216, k = it % 216, b = first + s;
@@ -505,25 +499,23 @@ SB_HD void pose_load(const PoseParams& P, int first, float* sm) {
     TILE_SYNC();
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void pose_forward_tile(const ModelView& M, const PoseParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
-    const SmallConsts C = stage_small_consts<S>(M, sm);
-    pose_load<S>(P, first, sm);
-    tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
+    const SmallConsts C = stage_small_consts<S, L>(M, sm);
+    pose_load<S, L>(P, first, sm);
+    tile_forward<S, L>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = first + s;
         if (P.joints && b < P.batch) P.joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
     }
-    tile_write_vertex_operands<S>(sm, first, P.batch, P.tc);
+    tile_write_vertex_operands<S, L>(sm, first, P.batch, P.tc);
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first, float* sm) {
-    using L = TileLayout<S>;
-    const SmallConsts C = stage_small_consts<S>(M, sm);
-    pose_load<S>(P, first, sm);
-    tile_forward<S>(M, C, sm, !P.rotmat_mode, false);
+    const SmallConsts C = stage_small_consts<S, L>(M, sm);
+    pose_load<S, L>(P, first, sm);
+    tile_forward<S, L>(M, C, sm, !P.rotmat_mode, false);
     FOR_ITEMS(it, S * 147) {
         const int s = it / 147, k = it % 147, b = first + s;
         sm[L::OUTJ + k * S + s] = (P.d_joints && b < P.batch) ? P.d_joints[(size_t)b * 147 + k] : 0.f;
@@ -542,11 +534,11 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
         }
     }
     TILE_SYNC();
-    ph_joint_backward<S>(M, C, sm);
+    ph_joint_backward<S, L>(M, C, sm);
     TILE_SYNC();
-    ph_pick_backward<S>(M, C, sm);
+    ph_pick_backward<S, L>(M, C, sm);
     TILE_SYNC();
-    ph_gemm_and_chain_backward<S>(M, sm);
+    ph_gemm_and_chain_backward<S, L>(M, sm);
     if (P.dx_part) {
         FOR_ITEMS(it, S * (kXPad / 4)) {
             const int s = it / (kXPad / 4), k4 = it % (kXPad / 4), b = first + s;
@@ -563,7 +555,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
     FOR_ITEMS(it, kJoints * S) {
         const int s = it % S, j = it / S, b = first + s;
         float g[9];
-        rotation_grad<S>(sm, j, s, g);
+        rotation_grad<S, L>(sm, j, s, g);
         if (b >= P.batch) continue;
         if (P.rotmat_mode) {
 #pragma unroll
@@ -578,7 +570,7 @@ SB_HD void pose_backward_tile(const ModelView& M, const PoseParams& P, int first
     }
     FOR_ITEMS(it, kBetas * S) {
         const int s = it % S, l = it / S, b = first + s;
-        const float g = beta_grad<S>(C, sm, l, s);
+        const float g = beta_grad<S, L>(C, sm, l, s);
         if (b < P.batch) P.d_betas[(size_t)b * kBetas + l] = g;
     }
 }

@@ -66,8 +66,9 @@ SB_HD float2 ld_const2(const float2* p) {
 #endif
 }
 
-template <int S>
+template <int S_>
 struct TileLayout {
+    static constexpr int S = S_;
     static constexpr int LDQ = S + 4;               // padded row of QT: conflict-free 16-byte column stores
     static constexpr int POSE = 0;                  // [72][S]
     static constexpr int BETA = POSE + 72 * S;      // [10][S]
@@ -94,6 +95,13 @@ struct TileLayout {
     static constexpr int SMEM_FLOATS = CONSTS + kSmallConstFloats;
     static_assert(kGauss * kPriorPad * S <= kQPad * LDQ, "prior scratch must fit in the QT region");
     static_assert(2 * kXPad * S <= kQPad * LDQ, "backward GEMM partials must fit in the QT region");
+    // index functions of the two arrays whose layout the GEMM implementation dictates (the pair kernel keeps them as
+    // tensor-core operands, fit_pair.cuh): Q / dQ [n][sample] and x [m][sample]
+    static constexpr bool kPair = false;
+    SB_HD static int q(int n, int s) { return QT + n * LDQ + s; }
+    SB_HD static int x(int m, int s) { return XT + m * S_ + s; }
+    SB_HD static void store_dq(float* sm, int n, int s, float v) { sm[q(n, s)] = v; }
+    SB_HD static void store_x(float* sm, int m, int s, float v) { sm[x(m, s)] = v; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -180,9 +188,8 @@ SB_HD float adam_update(float p, float g, float& m, float& v, const AdamConsts& 
 // ------------------------------------------------------------------------------------------------
 // Rotations of all joints from axis-angle + pose features / betas into x.  root_identity forces
 // R_0 = I (stage-1 hoisting: the rest pose every root rotation is applied to).
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_pose_features(float* sm, bool from_axis_angle, bool root_identity) {
-    using L = TileLayout<S>;
     FOR_ITEMS(it, kJoints * S) {
         const int s = it % S, j = it / S;
         float R[9];
@@ -200,21 +207,20 @@ SB_HD void ph_pose_features(float* sm, bool from_axis_angle, bool root_identity)
 #pragma unroll
         for (int e = 0; e < 9; ++e) {
             sm[L::RM + (j * 9 + e) * S + s] = R[e];
-            if (j > 0) sm[L::XT + (11 + (j - 1) * 9 + e) * S + s] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+            if (j > 0) L::store_x(sm, 11 + (j - 1) * 9 + e, s, R[e] - ((e % 4 == 0) ? 1.f : 0.f));
         }
     }
     FOR_ITEMS(it, (1 + kBetas + (kXPad - kX)) * S) {
         const int s = it % S, r = it / S;
-        if (r == 0) sm[L::XT + s] = 1.f;
-        else if (r <= kBetas) sm[L::XT + r * S + s] = sm[L::BETA + (r - 1) * S + s];
-        else sm[L::XT + (kX + r - 1 - kBetas) * S + s] = 0.f;
+        if (r == 0) L::store_x(sm, 0, s, 1.f);
+        else if (r <= kBetas) L::store_x(sm, r, s, sm[L::BETA + (r - 1) * S + s]);
+        else L::store_x(sm, kX + r - 1 - kBetas, s, 0.f);
     }
 }
 
 // J = J0 + JS.beta  (== J_regressor.(v_template + shapedirs.beta), folded in float64 at model creation)
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_rest_joints(const SmallConsts& C, float* sm) {
-    using L = TileLayout<S>;
     FOR_ITEMS(it, 72 * S) {
         const int s = it % S, jc = it / S;
         float a = C.J0[jc];
@@ -225,9 +231,8 @@ SB_HD void ph_rest_joints(const SmallConsts& C, float* sm) {
 }
 
 // World transforms level by level; also A_j^t = G_j^t - G_j^R J_j.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_chain_forward(const ModelView& M, float* sm, const Grp g) {
-    using L = TileLayout<S>;
     for (int lev = 0; lev < M.num_levels; ++lev) {
         const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
         FOR_ITEMS_G(it, cnt * S, g) {
@@ -423,13 +428,51 @@ SB_HD void gemm_item(int t, int& p, int& h) {
     else { p = t; h = 0; }
 }
 
+#if defined(SMPLB200_EMU_TS) && !defined(__CUDA_ARCH__)
+// TEST-ONLY numerics model of the tcgen05 3xTF32 path of the pair kernel (fit_pair.cuh), for the host emulation build:
+// operands split by truncation into the 19 bits the tensor core reads (hi) and the truncated remainder (lo); every MMA adds
+// the exact sum of its 8 products to the fp32 accumulator and TRUNCATES (what the tensor pipe was observed to do); hi.hi
+// products go to a `main` accumulator, the lo.hi and hi.lo corrections to a second one; `parts` partial accumulator pairs over
+// equal K ranges are added in fp32 at the end.
+#include <cmath>
+namespace tsemu {
+inline float trunc19(float v) { union { float f; unsigned u; } c; c.f = v; c.u &= 0xFFFFE000u; return c.f; }
+inline float trunc_f32(double v) { float f = (float)v; if (std::fabs((double)f) > std::fabs(v)) f = std::nextafterf(f, 0.f); return f; }
+// a[k], b[k] for k < K (K a multiple of 8 after zero padding by the caller)
+inline float dot3(const float* a, int astride, const float* b, int bstride, int K, int parts) {
+    const int ksteps = (K + 7) / 8, per = (ksteps + parts - 1) / parts;
+    float total = 0.f;
+    for (int p = 0; p < parts; ++p) {
+        float main = 0.f, corr = 0.f;
+        for (int ks = p * per; ks < ksteps && ks < (p + 1) * per; ++ks) {
+            double hh = 0, lh = 0, hl = 0;
+            for (int k = ks * 8; k < ks * 8 + 8 && k < K; ++k) {
+                const float av = a[(size_t)k * astride], bv = b[(size_t)k * bstride];
+                const float ah = trunc19(av), al = trunc19(av - ah), bh = trunc19(bv), bl = trunc19(bv - bh);
+                hh += (double)ah * bh; lh += (double)al * bh; hl += (double)ah * bl;
+            }
+            main = trunc_f32((double)main + hh);
+            corr = trunc_f32((double)corr + lh);
+            corr = trunc_f32((double)corr + hl);
+        }
+        total += main + corr;
+    }
+    return total;
+}
+}  // namespace tsemu
+#endif
+
 // QT[n][s] = sum_m Cf[m][n] * x[m][s]   (the folded joint GEMM: [S x 218] . [218 x 681])
 // S % 8 == 0: one thread owns 4 adjacent columns x 8 samples (32 accumulators, 1 LDG.128 + 2 LDS.128 per
 // 32 FMAs); the basis rows are streamed from L2 two groups of U rows ahead, x is broadcast from smem.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD_CALL void ph_fold_gemm_forward(const ModelView& M, float* sm) {
-    using L = TileLayout<S>;
     static_assert(S % 4 == 0, "S must be a multiple of 4");
+#if defined(SMPLB200_EMU_TS) && !defined(__CUDA_ARCH__)
+    for (int n = 0; n < kQPad; ++n)
+        for (int s = 0; s < S; ++s) sm[L::QT + n * L::LDQ + s] = tsemu::dot3(M.Cf + n, kQPad, sm + L::XT + s, S, kXPad, 1);
+    return;
+#endif
 #if defined(__CUDA_ARCH__)
     if constexpr (kSplitK<S>) {
         // called by the 352 GEMM threads of the standard tile (the chain warp is busy elsewhere): thread = (column quad, K half)
@@ -484,9 +527,17 @@ SB_HD_CALL void ph_fold_gemm_forward(const ModelView& M, float* sm) {
 // Device fast path (S a multiple of 8 or S = 12, >= 384 threads): thread = (n-range r of 3, sample group h, column quad mq of
 // 56), 4 x 8 accumulators; the three partial sums are combined in a fixed order through the (by then dead)
 // QT region - deterministic, no atomics.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
-    using L = TileLayout<S>;
+#if defined(SMPLB200_EMU_TS) && !defined(__CUDA_ARCH__)
+    {
+        float dx[kXPad * S];
+        for (int m = 0; m < kXPad; ++m)
+            for (int s = 0; s < S; ++s) dx[m * S + s] = tsemu::dot3(M.CfT + m, kXPad, sm + L::QT + s, L::LDQ, kQPad, SMPLB200_EMU_TS_BWD_PARTS);
+        for (int i = 0; i < kXPad * S; ++i) sm[L::XT + i] = dx[i];
+        return;
+    }
+#endif
 #if defined(__CUDA_ARCH__)
     if constexpr (kFastGemm<S>) {
         // n ranges: 3 x 232 rows with two sample groups; with one group the idle threads take more, shorter ranges
@@ -548,9 +599,8 @@ SB_HD_CALL void ph_fold_gemm_backward(const ModelView& M, float* sm) {
 // reprojection phase clears them) and are added in a fixed order when the outputs are gathered.
 constexpr int kHeavy = kExtra + kPicks;                 // 20 sources: picks 0..10, extras 11..19
 constexpr int kJointParts = 4;                         // the 24 joints in 4 runs of 6
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm) {
-    using L = TileLayout<S>;
     constexpr int JN = kJoints / kJointParts, EB = 5, PB = 3;
     constexpr int NEB = (kExtra + EB - 1) / EB, NPB = (kPicks + PB - 1) / PB;      // 2 extra blocks, 4 pick blocks
     static_assert(kHeavy * 3 * kJointParts <= 288, "partial positions must fit in the DG rows");
@@ -574,8 +624,7 @@ SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm)
                     const int k = k0 + i;
                     if (k < kExtra) {
                         const int qb = (k * kJoints + j) * 3;
-                        const float qx = sm[L::QT + (qb + 0) * L::LDQ + s], qy = sm[L::QT + (qb + 1) * L::LDQ + s],
-                                    qz = sm[L::QT + (qb + 2) * L::LDQ + s];
+                        const float qx = sm[L::q(qb + 0, s)], qy = sm[L::q(qb + 1, s)], qz = sm[L::q(qb + 2, s)];
                         const float w = C.wkj[k * kJoints + j];
                         acc[i][0] += g0 * qx + g1 * qy + g2 * qz + t0 * w;
                         acc[i][1] += g4 * qx + g5 * qy + g6 * qz + t1 * w;
@@ -597,7 +646,7 @@ SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm)
                 acc[i][0] = acc[i][1] = acc[i][2] = 0.f;
                 const int p = (p0 + i < kPicks) ? p0 + i : kPicks - 1;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[i][c] = sm[L::QT + (kQPickBase + 3 * p + c) * L::LDQ + s];
+                for (int c = 0; c < 3; ++c) v[i][c] = sm[L::q(kQPickBase + 3 * p + c, s)];
             }
             for (int j = t * JN; j < (t + 1) * JN; ++j) {
                 const float* G = sm + L::GW + (j * 12) * S + s;
@@ -642,9 +691,8 @@ SB_HD void ph_output_joints(const ModelView& M, const SmallConsts& C, float* sm)
 
 // Reprojection term of body_fitting_loss per output joint; with_grad also overwrites OUTJ with
 // dL/djoint.  LOSSJ[o] = conf^2 * (gmof(u - kx) + gmof(v - ky)).
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad) {
-    using L = TileLayout<S>;
     FOR_ITEMS(it, kOut * S) {
         const int s = it % S, o = it / S;
         const float Px = sm[L::OUTJ + (3 * o + 0) * S + s] + sm[L::CAM + 0 * S + s];
@@ -670,9 +718,17 @@ SB_HD void ph_reprojection(float* sm, float focal, float sigma2, bool with_grad)
 // ------------------------------------------------------------------------------------------------
 // Pd[(g,i)][s] = sum_j Psym_g[i][j] * bp[j][s] - (Psym_g mean_g)[i]   for all 8 components: an
 // [S x 72] . [72 x 576] GEMM streamed like the folded one (two adjacent i per thread).
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, float* sm) {
-    using L = TileLayout<S>;
+#if defined(SMPLB200_EMU_TS) && !defined(__CUDA_ARCH__)
+    for (int g = 0; g < kGauss; ++g)
+        for (int i = 0; i < kPriorPad; ++i)
+            for (int s = 0; s < S; ++s)
+                sm[L::QT + (g * kPriorPad + i) * S + s] =
+                    tsemu::dot3(M.gmm_prec + (size_t)g * kPriorPad * kPriorPad + i, kPriorPad, sm + L::POSE + 3 * S + s, S, kPriorPad, 1) -
+                    C.pmean[g * kPriorPad + i];
+    return;
+#endif
 #if defined(__CUDA_ARCH__)
     if constexpr (kSplitK<S>) {
         constexpr int IQ = kPriorPad / 4, KH = kPriorPad / 2, NI = kGauss * IQ;        // 144 (component, column quad) items x 2 K halves
@@ -754,9 +810,8 @@ SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, flo
     }
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, float prior_w2, float angle_w2, float shape_w2) {
-    using L = TileLayout<S>;
     FOR_ITEMS(it, kGauss * S) {
         const int s = it % S, g = it / S;
         float q = 0.f;
@@ -802,9 +857,8 @@ SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, 
 // ------------------------------------------------------------------------------------------------
 // backward phases
 // ------------------------------------------------------------------------------------------------
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void source_grad(const ModelView& M, const float* sm, int src, int s, float* d) {
-    using L = TileLayout<S>;
     d[0] = d[1] = d[2] = 0.f;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -819,15 +873,14 @@ SB_HD void source_grad(const ModelView& M, const float* sm, int src, int s, floa
 
 // Gradients arriving at the 20 heavy source joints (kHeavy: picks 0..10, extras 11..19), gathered once per sample into the
 // XT rows - x is dead between the forward and the backward folded GEMM - instead of once per (joint, source).
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_source_grads(const ModelView& M, float* sm) {
-    using L = TileLayout<S>;
     static_assert(kHeavy * 3 <= kXPad, "source gradients must fit in the XT rows");
     FOR_ITEMS(it, kHeavy * S) {
         const int s = it % S, h = it / S;
         const int src = (h < kPicks) ? kJoints + h : kJoints + kSelVerts + (h - kPicks);
         float d[3];
-        source_grad<S>(M, sm, src, s, d);
+        source_grad<S, L>(M, sm, src, s, d);
 #pragma unroll
         for (int c = 0; c < 3; ++c) sm[L::XT + (3 * h + c) * S + s] = d[c];
     }
@@ -835,10 +888,9 @@ SB_HD void ph_source_grads(const ModelView& M, float* sm) {
 
 // dL/dA_j from the extra joints and the picked vertices, converted to dL/dG_j and dL/dJ_j.  DG holds additional dL/dA
 // rows on entry (zero in the fit, the vertex path's dA in SMPL backward).  Starts with ph_source_grads + a tile barrier.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm) {
-    using L = TileLayout<S>;
-    ph_source_grads<S>(M, sm);
+    ph_source_grads<S, L>(M, sm);
     TILE_SYNC();
     const float* SG = sm + L::XT;
     FOR_ITEMS(it, kJoints * S) {
@@ -856,25 +908,22 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
         for (int k = 0; k < kExtra; ++k) {
             const float dE[3] = {SG[(3 * (kPicks + k) + 0) * S + s], SG[(3 * (kPicks + k) + 1) * S + s], SG[(3 * (kPicks + k) + 2) * S + s]};
             const int qb = (k * kJoints + j) * 3;
-            float* q0 = sm + L::QT + (qb + 0) * L::LDQ + s;
-            float* q1 = sm + L::QT + (qb + 1) * L::LDQ + s;
-            float* q2 = sm + L::QT + (qb + 2) * L::LDQ + s;
-            const float qx = *q0, qy = *q1, qz = *q2;
+            const float qx = sm[L::q(qb + 0, s)], qy = sm[L::q(qb + 1, s)], qz = sm[L::q(qb + 2, s)];
             const float w = C.wkj[k * kJoints + j];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 dAR[r * 3 + 0] += dE[r] * qx; dAR[r * 3 + 1] += dE[r] * qy; dAR[r * 3 + 2] += dE[r] * qz;
                 dAt[r] += w * dE[r];
             }
-            *q0 = G[0] * dE[0] + G[3] * dE[1] + G[6] * dE[2];
-            *q1 = G[1] * dE[0] + G[4] * dE[1] + G[7] * dE[2];
-            *q2 = G[2] * dE[0] + G[5] * dE[1] + G[8] * dE[2];
+            L::store_dq(sm, qb + 0, s, G[0] * dE[0] + G[3] * dE[1] + G[6] * dE[2]);
+            L::store_dq(sm, qb + 1, s, G[1] * dE[0] + G[4] * dE[1] + G[7] * dE[2]);
+            L::store_dq(sm, qb + 2, s, G[2] * dE[0] + G[5] * dE[1] + G[8] * dE[2]);
         }
         for (int p = 0; p < kPicks; ++p) {
             const float dV[3] = {SG[(3 * p + 0) * S + s], SG[(3 * p + 1) * S + s], SG[(3 * p + 2) * S + s]};
             const float w = C.Wp[p * kJoints + j];
-            const float vx = sm[L::QT + (kQPickBase + 3 * p + 0) * L::LDQ + s], vy = sm[L::QT + (kQPickBase + 3 * p + 1) * L::LDQ + s],
-                        vz = sm[L::QT + (kQPickBase + 3 * p + 2) * L::LDQ + s];
+            const float vx = sm[L::q(kQPickBase + 3 * p + 0, s)], vy = sm[L::q(kQPickBase + 3 * p + 1, s)],
+                        vz = sm[L::q(kQPickBase + 3 * p + 2, s)];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const float wd = w * dV[r];
@@ -885,7 +934,7 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
         // A^R = G^R ; A^t = G^t - G^R J
         const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s], Jz = sm[L::JR + (3 * j + 2) * S + s];
         float dJt[3];
-        source_grad<S>(M, sm, j, s, dJt);           // the chain joint itself is G_j^t
+        source_grad<S, L>(M, sm, j, s, dJt);           // the chain joint itself is G_j^t
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             sm[L::DG + (j * 12 + r * 4 + 0) * S + s] = dAR[r * 3 + 0] - dAt[r] * Jx;
@@ -901,9 +950,8 @@ SB_HD void ph_joint_backward(const ModelView& M, const SmallConsts& C, float* sm
 
 // dL/d(v_posed of picked vertex) = (sum_j Wp[p][j] G_j^R)^T dL/dvert ; written over the pick rows of QT.  Reads the source
 // gradients ph_joint_backward left in XT; runs after it (a tile barrier in between: it overwrites the pick rows that phase reads).
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_pick_backward(const ModelView& M, const SmallConsts& C, float* sm) {
-    using L = TileLayout<S>;
     const float* SG = sm + L::XT;
     FOR_ITEMS(it, kPicks * S) {
         const int s = it % S, p = it / S;
@@ -920,16 +968,15 @@ SB_HD void ph_pick_backward(const ModelView& M, const SmallConsts& C, float* sm)
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            sm[L::QT + (kQPickBase + 3 * p + c) * L::LDQ + s] = T[0 + c] * dV[0] + T[3 + c] * dV[1] + T[6 + c] * dV[2];
+            L::store_dq(sm, kQPickBase + 3 * p + c, s, T[0 + c] * dV[0] + T[3 + c] * dV[1] + T[6 + c] * dV[2]);
     }
 }
 
 // Reverse sweep of the kinematic chain.  Parents gather from their children level by level
 // (deterministic, no atomics); then every joint derives dL/dR_j (stored over RM) and the
 // rest-joint gradient DJ.
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void ph_chain_backward(const ModelView& M, float* sm, const Grp g) {
-    using L = TileLayout<S>;
     for (int lev = M.num_levels - 2; lev >= 0; --lev) {
         const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
         FOR_ITEMS_G(it, cnt * S, g) {
@@ -1005,9 +1052,8 @@ SB_HD void ph_chain_backward(const ModelView& M, float* sm, const Grp g) {
 }
 
 // dL/dR_j of body joints also receives the pose-feature gradient dx[11 + 9(j-1) + e].
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void rotation_grad(const float* sm, int j, int s, float* g) {
-    using L = TileLayout<S>;
 #pragma unroll
     for (int e = 0; e < 9; ++e) {
         g[e] = sm[L::RM + (j * 9 + e) * S + s];
@@ -1016,15 +1062,14 @@ SB_HD void rotation_grad(const float* sm, int j, int s, float* g) {
 }
 
 // dL/dbeta_l = dx[1+l] + sum_{j,c} JS[j][c][l] dJ[j][c]  (the prior term is added by the caller)
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD float beta_grad(const SmallConsts& C, const float* sm, int l, int s) {
-    using L = TileLayout<S>;
     float a = sm[L::XT + (1 + l) * S + s];
     for (int jc = 0; jc < 72; ++jc) a += C.JS[jc * kBetas + l] * sm[L::DJ + jc * S + s];
     return a;
 }
 
-template <int S>
+template <int S, class L = TileLayout<S>>
 SB_HD void zero_rows(float* sm, int off, int rows) {
     FOR_ITEMS(it, rows * S) sm[off + it] = 0.f;
 }

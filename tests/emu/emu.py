@@ -10,7 +10,7 @@ from inbed_pose_estimation_b200 import _native, synthetic
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LIB = os.path.join(HERE, 'libsmplify_emu.so')
+LIB = os.environ.get('SMPLB200_EMU_LIB') or os.path.join(HERE, 'libsmplify_emu.so')   # override: numerics experiments
 _vp, _ci, _cf, _cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double
 
 
@@ -19,6 +19,8 @@ def available():
 
 
 def _build():
+    if os.environ.get('SMPLB200_EMU_LIB'):
+        return
     csrc = _native.CSRC
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(HERE, 'emu_api.cu')]
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
