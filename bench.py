@@ -464,7 +464,10 @@ def run_ours(a):
         # which fit kernel ran
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         n16, small, n_small = _native.fit_tile_plan(B, sms)
-        if n16 and n_small:
+        pairs, p16, p12 = _native.fit_pair_plan(B, sms)
+        if pairs:
+            fit_kernel = 'smplify_fit_pair_kernel<16,12> (%d pairs of 2 x 16 + %d pairs of 2 x 12 samples, 2-CTA clusters)' % (p16, p12)
+        elif n16 and n_small:
             fit_kernel = 'smplify_fit_mixed_kernel<16,%d> (%d x 16 + %d x %d samples)' % (small, n16, n_small, small)
         else:
             fit_kernel = 'smplify_fit_kernel<%d>' % (16 if n16 else small)

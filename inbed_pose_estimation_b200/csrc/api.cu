@@ -79,6 +79,14 @@ extern "C" void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small,
     if (small) *small = b;
     if (n_small) *n_small = c;
 }
+extern "C" int smplb200_fit_pair_plan(int batch, int sms, int* n16, int* n12) {
+    int a = 0, b = 0;
+    const int pairs = fit_uses_pairs(batch, 1);
+    if (pairs && sms > 1) plan_fit_pairs(batch, sms, &a, &b);
+    if (n16) *n16 = a;
+    if (n12) *n12 = b;
+    return pairs;
+}
 extern "C" const char* smplb200_last_error(void) { return g_error.c_str(); }
 #if defined(SMPLB200_PHASE_CLOCKS)
 // profiling builds only (tools/phase_clocks.py): read / reset the stage-2 phase cycle counters
@@ -86,6 +94,11 @@ namespace smplb200 { cudaError_t debug_phase_clocks(unsigned long long* out32, i
 extern "C" int smplb200_debug_phase_clocks(unsigned long long* out32, int reset) {
     return smplb200::debug_phase_clocks(out32, reset) == cudaSuccess ? 0 : 1;
 }
+#endif
+
+#if defined(PG_TRACE)
+namespace smplb200 { cudaError_t debug_pg_trace(long long* out512); }
+extern "C" int smplb200_debug_pg_trace(long long* out512) { return smplb200::debug_pg_trace(out512) == cudaSuccess ? 0 : 1; }
 #endif
 
 extern "C" long long smplb200_launch_count(int reset) {
@@ -134,6 +147,9 @@ extern "C" int smplb200_model_create(const smplb200_model_desc* desc, int device
     rc |= upload(m, H.gmm_prec, &m->view.gmm_prec);
     rc |= upload(m, H.gmm_pmean, &m->view.gmm_pmean);
     rc |= upload(m, H.gmm_lognll, &m->view.gmm_lognll);
+    rc |= upload(m, H.pg_prior, &m->view.pg_prior);
+    rc |= upload(m, H.pg_fwd, &m->view.pg_fwd);
+    rc |= upload(m, H.pg_bwd, &m->view.pg_bwd);
     const float *bt_hi = nullptr, *bt_lo = nullptr, *bm_hi = nullptr, *bm_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr,
                 *wT_hi = nullptr, *wT_lo = nullptr;
     rc |= upload(m, H.basisT_hi, &bt_hi);

@@ -32,11 +32,13 @@ namespace smplb200 {
 
 // The threads that execute a phase: the whole tile (block barrier between sub-steps) or a single warp (warp barrier).
 // The latency-bound kinematic-chain sweeps run on the one warp the folded GEMMs leave idle, concurrently with them.
+// warp_only: 0 = the whole tile (block barrier), 1 = one warp, 2 = a group of whole warps meeting on named barrier 2
 struct Grp { int tid, nt, warp_only; };
 SB_HD Grp grp_tile() { return Grp{TILE_TID, TILE_NT, 0}; }
 SB_HD void grp_sync(const Grp& g) {
 #if defined(__CUDA_ARCH__)
-    if (g.warp_only) __syncwarp();
+    if (g.warp_only == 1) __syncwarp();
+    else if (g.warp_only == 2) asm volatile("bar.sync 2, %0;" ::"r"(g.nt) : "memory");
     else __syncthreads();
 #else
     (void)g;
@@ -100,6 +102,7 @@ struct TileLayout {
     static constexpr bool kPair = false;
     SB_HD static int q(int n, int s) { return QT + n * LDQ + s; }
     SB_HD static int x(int m, int s) { return XT + m * S_ + s; }
+    SB_HD static int pd(int g, int i, int s) { return QT + (g * kPriorPad + i) * S_ + s; }      // prior scratch Psym (bp - mean)
     SB_HD static void store_dq(float* sm, int n, int s, float v) { sm[q(n, s)] = v; }
     SB_HD static void store_x(float* sm, int m, int s, float v) { sm[x(m, s)] = v; }
 };
@@ -811,16 +814,17 @@ SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, flo
 }
 
 template <int S, class L = TileLayout<S>>
-SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, float prior_w2, float angle_w2, float shape_w2) {
-    FOR_ITEMS(it, kGauss * S) {
+SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, float prior_w2, float angle_w2, float shape_w2,
+                           const Grp grp = grp_tile()) {
+    FOR_ITEMS_G(it, kGauss * S, grp) {
         const int s = it % S, g = it / S;
         float q = 0.f;
         for (int i = 0; i < kPriorDim; ++i)
-            q += sm[L::QT + (g * kPriorPad + i) * S + s] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
+            q += sm[L::pd(g, i, s)] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
         sm[L::MISC + g * S + s] = 0.5f * q - C.lognll[g];
     }
-    TILE_SYNC();
-    FOR_ITEMS(s, S) {
+    grp_sync(grp);
+    FOR_ITEMS_G(s, S, grp) {
         int best = 0;
         float bv = sm[L::MISC + s];
         for (int g = 1; g < kGauss; ++g) {
@@ -839,12 +843,12 @@ SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, 
         for (int l = 0; l < kBetas; ++l) sh += sm[L::BETA + l * S + s] * sm[L::BETA + l * S + s];
         sm[L::LOSSJ + 51 * S + s] = shape_w2 * sh;
     }
-    TILE_SYNC();
+    grp_sync(grp);
     // gradient of the selected component: prior_w2 * Psym (bp - mean); plus the angle prior
-    FOR_ITEMS(it, kPriorDim * S) {
+    FOR_ITEMS_G(it, kPriorDim * S, grp) {
         const int s = it % S, i = it / S;
         const int g = (int)sm[L::MISC + 8 * S + s];
-        float gr = prior_w2 * sm[L::QT + (g * kPriorPad + i) * S + s];
+        float gr = prior_w2 * sm[L::pd(g, i, s)];
         for (int k = 0; k < 4; ++k)
             if (M.angle_ids[k] == i) {
                 const float e = expf(sm[L::POSE + (3 + i) * S + s] * M.angle_signs[k]);

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include "fit_driver.cuh"
+#include "fit_pair.cuh"
 #include "launch.h"
 
 namespace smplb200 {
@@ -34,6 +35,19 @@ __global__ void __launch_bounds__(kFitThreads, 1) smplify_fit_mixed_kernel(const
     const int blk = blockIdx.x;                                  // block-uniform branch
     if (blk < n_a) fit_tile<SA>(M, P, blk * SA, sm);
     else fit_tile<SB>(M, P, n_a * SA + (blk - n_a) * SB, sm);
+}
+
+// Pairs of CTAs (2-CTA clusters) that share their GEMMs on the tensor cores (fit_pair.cuh): pairs [0, n_a) fit 2 x SA samples,
+// the others 2 x SB, starting where the first group ends.  One CTA per SM; a wave is sms / 2 pairs.
+template <int SA, int SB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pg::kThreads, 1)
+    smplify_fit_pair_kernel(const __grid_constant__ ModelView M, const __grid_constant__ FitParams P, int n_a) {
+    extern __shared__ __align__(16) float sm_raw[];
+    float* sm = sm_raw + ((1024u - (tc::smem_u32(sm_raw) & 1023u)) & 1023u) / 4;          // SWIZZLE_128B atoms: 1024-byte aligned
+    const uint32_t rank = tc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1;
+    if (pair < n_a) fit_pair_tile<SA>(M, P, pair * 2 * SA + (int)rank * SA, sm, rank);
+    else fit_pair_tile<SB>(M, P, n_a * 2 * SA + (pair - n_a) * 2 * SB + (int)rank * SB, sm, rank);
 }
 
 template <int S>
@@ -78,6 +92,13 @@ static cudaError_t opt_in_smem(K kernel, size_t bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+#if defined(PG_TRACE)
+cudaError_t debug_pg_trace(long long* out512) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(out512, pg::g_pg_trace, sizeof(long long) * 512);
+    return e;
+}
+#endif
 #if defined(SMPLB200_PHASE_CLOCKS)
 cudaError_t debug_phase_clocks(unsigned long long* out32, int reset) {
     cudaError_t e = cudaDeviceSynchronize();
@@ -123,9 +144,47 @@ static cudaError_t launch_fit_mixed(const ModelView& M, const FitParams& P, int 
     return cudaGetLastError();
 }
 
+// Pair plan of a batch: n16 pairs of 2 x 16 samples in whole waves of sms / 2 pairs, the remainder as pairs of 2 x 12 when
+// one wave of those covers it, else as more pairs of 2 x 16.
+void plan_fit_pairs(int batch, int sms, int* n16, int* n12) {
+    const int wave = sms / 2;
+    const int full = batch / (32 * wave);
+    const int rest = batch - full * 32 * wave;
+    *n16 = full * wave;
+    *n12 = 0;
+    if (rest == 0) return;
+    if ((rest + 23) / 24 <= wave) *n12 = (rest + 23) / 24;
+    else *n16 += (rest + 31) / 32;
+}
+
+static cudaError_t launch_fit_pairs(const ModelView& M, const FitParams& P, int sms, cudaStream_t stream) {
+    int n16 = 0, n12 = 0;
+    plan_fit_pairs(P.batch, sms, &n16, &n12);
+    const size_t smem = (size_t)(PairLayout<16>::SMEM_FLOATS > PairLayout<12>::SMEM_FLOATS ? PairLayout<16>::SMEM_FLOATS
+                                                                                          : PairLayout<12>::SMEM_FLOATS) * sizeof(float) + 1024;
+    cudaError_t e = opt_in_smem(smplify_fit_pair_kernel<16, 12>, smem);
+    if (e != cudaSuccess) return e;
+    smplify_fit_pair_kernel<16, 12><<<2 * (n16 + n12), pg::kThreads, smem, stream>>>(M, P, n16);
+    return cudaGetLastError();
+}
+
+// Batches from this size on run on the pair kernel (tensor-core GEMMs shared by two CTAs); smaller ones on the 4- / 8-sample
+// tiles of the CUDA-core kernel, which fill more SMs.
+constexpr int kPairMinBatch = 1024;
+
+static int fit_variant() {
+    static const int variant = [] { const char* v = getenv("SMPLB200_FIT_VARIANT"); return v ? atoi(v) : 0; }();   // experiments only
+    return variant;
+}
+int fit_uses_pairs(int batch, int num_iters) {
+    const int variant = fit_variant();
+    return (variant == 10 || (variant == 0 && num_iters > 0 && batch >= kPairMinBatch)) ? 1 : 0;
+}
+
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream) {
     if (P.batch <= 0) return cudaSuccess;
-    static const int variant = [] { const char* v = getenv("SMPLB200_FIT_VARIANT"); return v ? atoi(v) : 0; }();   // experiments only
+    const int variant = fit_variant();
+    if (fit_uses_pairs(P.batch, P.num_iters) && M.pg_fwd != nullptr) return launch_fit_pairs(M, P, device_sm_count(), stream);
     if (variant == 1) return launch_fit_variant<8, 192, 2>(M, P, stream);
     if (variant == 2) return launch_fit_variant<8, 256, 2>(M, P, stream);
     if (variant == 3) return launch_fit_variant<16, 384, 1>(M, P, stream);

@@ -235,6 +235,25 @@ std::string build_host_model(const smplb200_model_desc& d, HostModel& H) {
             H.gmm_lognll[g] = (float)log((double)d.gmm_nll_weights[g]);
         }
     }
+    // ---- packed A operands of the pair kernel's tensor-core GEMMs -----------------------------------------------------
+    // element (row R of the tile space, k) of a GEMM with KC chunks sits at float index
+    //   ((((t * 2 + h) * KC + k / 32) * 8 + (k % 32) / 4) * 128 + r) * 4 + k % 4,    R = 256 t + 128 h + r
+    auto pack = [](std::vector<float>& out, int tiles, int kchunks, int rows, int K, const std::function<float(int, int)>& at) {
+        out.assign((size_t)tiles * 2 * kchunks * kPgChunk * 128, 0.f);
+        for (int R = 0; R < rows; ++R) {
+            const int t = R / 256, h = (R % 256) / 128, r = R % 128;
+            for (int k = 0; k < K; ++k) {
+                const size_t idx = ((((size_t)(t * 2 + h) * kchunks + k / kPgChunk) * 8 + (k % kPgChunk) / 4) * 128 + r) * 4 + k % 4;
+                out[idx] = at(R, k);
+            }
+        }
+    };
+    pack(H.pg_fwd, kPgFwdTiles, kPgFwdChunks, kQPad, kXPad, [&](int n, int m) { return H.Cf[(size_t)m * kQPad + n]; });
+    pack(H.pg_bwd, kPgBwdTiles, kPgBwdChunks, kXPad, kQPad, [&](int m, int n) { return H.Cf[(size_t)m * kQPad + n]; });
+    pack(H.pg_prior, kPgPriorTiles, kPgPriorChunks, kGauss * kPriorPad, kPriorPad, [&](int R, int j) {
+        const int g = R / kPriorPad, i = R % kPriorPad;
+        return H.gmm_prec[(size_t)g * kPriorPad * kPriorPad + (size_t)j * kPriorPad + i];
+    });
     return std::string();
 }
 

@@ -54,6 +54,9 @@ struct ModelView {
     const float* gmm_prec;   // [8][72 j][72 i]    symmetrised precision, i fastest, zero padded
     const float* gmm_pmean;  // [8][72]            prec_sym . mean
     const float* gmm_lognll; // [8]                log(nll_weights)
+    const float* pg_prior;   // packed A operands of the pair kernel's GEMMs (kPg*Floats): symmetrised precisions,
+    const float* pg_fwd;     //   Cf^T (rows n, k = m),
+    const float* pg_bwd;     //   Cf   (rows m, k = n)
     int32_t pick_vid[kSelVerts];
     int8_t parents[kJoints];
     uint8_t joint_map[kOut];
@@ -75,6 +78,16 @@ struct AdamScalars {           // per-iteration host-computed scalars (torch com
     float step_size;           // lr / (1 - beta1^t)
     float bc2_sqrt;            // sqrt(1 - beta2^t)
 };
+
+// Shapes of the pair fit kernel's tensor-core GEMMs (pair_gemm.cuh): 256-row tiles (128 rows per CTA of the pair), chunks
+// of 32 k values.  Packed constant arrays: [tile][half][k chunk][8 float4 of a row][128 rows] float4.
+constexpr int kPgChunk = 32;
+constexpr int kPgPriorTiles = 3, kPgPriorChunks = 3;                       // 576 rows (g, i), K = 72 (zero padded to 96)
+constexpr int kPgFwdTiles = 3, kPgFwdChunks = kXPad / kPgChunk;            // 704 rows n, K = 224
+constexpr int kPgBwdTiles = 1, kPgBwdChunks = kQPad / kPgChunk;            // 224 rows m, K = 704
+constexpr size_t kPgPriorFloats = (size_t)kPgPriorTiles * 2 * kPgPriorChunks * kPgChunk * 128;
+constexpr size_t kPgFwdFloats = (size_t)kPgFwdTiles * 2 * kPgFwdChunks * kPgChunk * 128;
+constexpr size_t kPgBwdFloats = (size_t)kPgBwdTiles * 2 * kPgBwdChunks * kPgChunk * 128;
 
 constexpr int kFitTileThreads = 384; // threads of the standard tile (fit and pose kernels)
 constexpr int kMaxIters = 256;     // per stage; bounds the in-kernel Adam scalar table

@@ -20,10 +20,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU.
+// Bounded wait: a protocol bug must trap, not hang the GPU.  (A try_wait that does not succeed returns after a hardware time
+// limit of the order of a microsecond: 2^22 attempts are seconds.)
+#if !defined(SMPLB200_SPIN_LOG2)
+#define SMPLB200_SPIN_LOG2 22
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << SMPLB200_SPIN_LOG2); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

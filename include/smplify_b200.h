@@ -239,6 +239,12 @@ int smplb200_smplify_fit_host(const smplb200_model* model, int batch, int num_it
  * samples followed by n_small tiles of `small` (4, 8 or 12; 0 = none) samples.  Pure host arithmetic. */
 void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_small);
 
+/* Batches of 1024 samples and more run on the PAIR kernel: 2-CTA clusters of 2 x 16 (or, in the last wave, 2 x 12) samples
+ * that share the per-iteration GEMMs on the tensor cores (tcgen05 cta_group::2, 3xTF32).  Returns 1 if smplb200_smplify_fit
+ * uses it for `batch` (then n16 / n12 = the numbers of 2 x 16- and 2 x 12-sample pairs on `sms` SMs), else 0 (the tile plan
+ * above applies).  Pure host arithmetic. */
+int smplb200_fit_pair_plan(int batch, int sms, int* n16, int* n12);
+
 /* Number of this library's kernel launches issued by the process (any thread: torch autograd runs backward calls on
  * its own threads) since the last reset; reset != 0 returns the count and clears it (bench.py reports it as gpu_launches). */
 long long smplb200_launch_count(int reset);

@@ -26,6 +26,7 @@ else:
     ap.add_argument('cmd')
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--iters', type=int, default=100)
+    ap.add_argument('--pair', action='store_true', help='slot names of the pair kernel (fit_pair.cuh)')
     a = ap.parse_args()
     lib = _native.lib()
     fitter = synthetic.build_smplify('cuda', num_iters=a.iters, seed=0)
@@ -37,7 +38,25 @@ else:
         fitter(args[0], args[1], args[2], args[3], args[4].clone())
         torch.cuda.synchronize()
     lib.smplb200_debug_phase_clocks(buf, 0)
-    tot = sum(buf[i] for i in range(12))
-    print('stage-2 cycles per iteration (CTA 0): %.0f' % (tot / a.iters))
-    for i, n in enumerate(NAMES):
-        print('%-42s %9.0f clk/iter  %5.1f%%' % (n, buf[i] / a.iters, 100.0 * buf[i] / tot))
+    if a.pair:
+        names = {0: 'pose features + rest joints + B operands', 1: 'cluster barrier before the forward call', 2: 'forward call: generator warp 0 busy',
+                 3: 'forward call: wait for the end barrier (gen warp 0)', 4: '49 output joints', 5: 'projection + GMoF', 6: 'joint backward',
+                 7: 'picked-vertex backward', 8: 'cluster barrier before the backward call', 9: 'backward call: generator warp 0 busy',
+                 10: 'backward call: wait for the end barrier (gen warp 0)', 11: 'Rodrigues backward + Adam',
+                 16: '  [forward call] generator warp 4', 17: '  [forward call] epilogue warp 8 (incl. prior select)', 18: '  [forward call] MMA warp',
+                 19: '  [forward call] chain warp', 20: '  [backward call] generator warp 4', 21: '  [backward call] epilogue warp 8',
+                 22: '  [backward call] MMA warp', 23: '  [backward call] chain warp',
+                 24: '  [forward call] generator warp 0: waiting for a ring slot', 25: '  [forward call] generator warp 0: TMEM store + publish',
+                 26: '  [forward call] MMA warp: waiting for chunks', 28: '  [backward call] generator warp 0: waiting for a ring slot',
+                 29: '  [backward call] generator warp 0: TMEM store + publish', 30: '  [backward call] MMA warp: waiting for chunks'}
+        n_fwd = a.iters + 2                                   # the stage-1 prologue and the final forward also make a forward call
+        tot = sum(buf[i] for i in range(12))
+        print('pair kernel, CTA 0: %.0f cycles per stage-2 iteration (thread 0; forward-call slots include the 2 extra calls)' % (tot / a.iters))
+        for i in sorted(names):
+            per = a.iters if (i in (4, 5, 6, 7, 11) or 8 <= i <= 10 or 20 <= i <= 23 or i >= 28) else n_fwd
+            print('%-58s %9.0f clk/call' % (names[i], buf[i] / per))
+    else:
+        tot = sum(buf[i] for i in range(12))
+        print('stage-2 cycles per iteration (CTA 0): %.0f' % (tot / a.iters))
+        for i, n in enumerate(NAMES):
+            print('%-42s %9.0f clk/iter  %5.1f%%' % (n, buf[i] / a.iters, 100.0 * buf[i] / tot))
