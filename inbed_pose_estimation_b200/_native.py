@@ -220,6 +220,8 @@ def _declare(lib):
     lib.smplb200_weak_perspective_projection.argtypes = [ci, ci, vp, vp, cf, cf, vp, vp, vp]
     lib.smplb200_weak_perspective_projection_backward.restype = ci
     lib.smplb200_weak_perspective_projection_backward.argtypes = [ci, ci, vp, vp, cf, cf, vp, vp, vp, vp, vp]
+    lib.smplb200_fit_split_plan.restype = ci
+    lib.smplb200_fit_split_plan.argtypes = [ci, ci]
     lib.smplb200_fit_pair_plan.restype = ci
     lib.smplb200_fit_pair_plan.argtypes = [ci, ci] + [ctypes.POINTER(ci)] * 2
     lib.smplb200_fit_tile_plan.restype = None
@@ -239,7 +241,7 @@ EXPORTED_SYMBOLS = (
     'smplb200_fits_set', 'smplb200_keep_better', 'smplb200_finalize_fits', 'smplb200_train_loss_workspace_bytes',
     'smplb200_fit_tile_plan', 'smplb200_weak_perspective_projection', 'smplb200_weak_perspective_projection_backward',
     'smplb200_smpl_param_losses', 'smplb200_keypoint_loss', 'smplb200_keypoint_3d_loss', 'smplb200_shape_loss',
-    'smplb200_prior_terms', 'smplb200_probe_tf32_peak', 'smplb200_fit_pair_plan',
+    'smplb200_prior_terms', 'smplb200_probe_tf32_peak', 'smplb200_fit_pair_plan', 'smplb200_fit_split_plan',
 )
 
 
@@ -259,6 +261,11 @@ def fit_tile_plan(batch, sms=148):
     a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
     lib().smplb200_fit_tile_plan(int(batch), int(sms), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
     return a.value, b.value, c.value
+
+
+def fit_split_plan(batch, sms=148):
+    """CTAs per 4-sample tile of the small-batch cluster kernel for this batch (8 / 4 / 2), 0 = the tile kernels run it."""
+    return int(lib().smplb200_fit_split_plan(int(batch), int(sms)))
 
 
 def fit_pair_plan(batch, sms=148):

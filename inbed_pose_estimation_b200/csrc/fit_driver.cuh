@@ -242,6 +242,76 @@ SB_HD void tile_zero_ignored_conf(const ModelView& M, const FitParams& P, int fi
     }
 }
 
+// One Adam step of stage 2 on the tile's 72 pose entries and 10 betas: chain rule through the rotations (dL/dR from the chain
+// sweep + dL/dx of the folded GEMM, in XT) and the shape features, plus the prior gradients.
+template <int S, class L = TileLayout<S>>
+SB_HD void tile_adam_step(const SmallConsts& C, const FitParams& P, float* sm, const AdamScalars& sc) {
+    FOR_ITEMS(itj, kJoints * S) {
+        const int s = itj % S, j = itj / S;
+        float g[9], d[3];
+        rotation_grad<S, L>(sm, j, s, g);
+        rodrigues_bwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
+                      sm[L::POSE + (3 * j + 2) * S + s], g, d);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int k = 3 * j + a;
+            if (j > 0) d[a] += sm[L::GPR + (k - 3) * S + s];
+            sm[L::POSE + k * S + s] = adam_update(sm[L::POSE + k * S + s], d[a], sm[L::ADM + k * S + s],
+                                                  sm[L::ADV + k * S + s], P.adam_c, sc);
+        }
+    }
+    FOR_ITEMS(itb, kBetas * S) {
+        const int s = itb % S, l = itb / S;
+        const float beta = sm[L::BETA + l * S + s];
+        const float g = beta_grad<S, L>(C, sm, l, s) + 2.f * kShapePriorW2 * beta;
+        sm[L::BETA + l * S + s] = adam_update(beta, g, sm[L::ADM + (72 + l) * S + s], sm[L::ADV + (72 + l) * S + s],
+                                              P.adam_c, sc);
+    }
+}
+
+// Results of a tile whose final forward has been run: joints, operands of the vertex kernels, per-joint reprojection loss,
+// parameters, packed rows.  Contains tile barriers: the whole tile calls it.
+template <int S, class L = TileLayout<S>>
+SB_HD void tile_write_outputs(const FitParams& P, int first, float* sm) {
+    FOR_ITEMS(it, S * 147) {
+        const int s = it / 147, k = it % 147, b = first + s;
+        if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
+    }
+    tile_write_vertex_operands<S, L>(sm, first, P.batch, P.tc);
+    TILE_SYNC();
+    ph_reprojection<S, L>(sm, P.focal, kSigma2, false);
+    TILE_SYNC();
+    FOR_ITEMS(it, S * kOut) {
+        const int s = it / kOut, o = it % kOut, b = first + s;
+        if (b < P.batch) P.out_reproj[(size_t)b * kOut + o] = sm[L::LOSSJ + o * S + s];
+    }
+    FOR_ITEMS(it, S * 72) {
+        const int s = it / 72, k = it % 72, b = first + s;
+        if (P.out_pose && b < P.batch) P.out_pose[(size_t)b * 72 + k] = sm[L::POSE + k * S + s];
+    }
+    FOR_ITEMS(it, S * kBetas) {
+        const int s = it / kBetas, k = it % kBetas, b = first + s;
+        if (P.out_betas && b < P.batch) P.out_betas[(size_t)b * kBetas + k] = sm[L::BETA + k * S + s];
+    }
+    FOR_ITEMS(it, S * 3) {
+        const int s = it / 3, k = it % 3, b = first + s;
+        if (P.out_cam && b < P.batch) P.out_cam[(size_t)b * 3 + k] = sm[L::CAM + k * S + s];
+    }
+    if (P.out_packed) {
+        constexpr int kPacked = 72 + kBetas + 3 + kOut;
+        FOR_ITEMS(it, S * kPacked) {
+            const int s = it / kPacked, k = it % kPacked, b = first + s;
+            if (b >= P.batch) continue;
+            float v;
+            if (k < 72) v = sm[L::POSE + k * S + s];
+            else if (k < 72 + kBetas) v = sm[L::BETA + (k - 72) * S + s];
+            else if (k < 72 + kBetas + 3) v = sm[L::CAM + (k - 72 - kBetas) * S + s];
+            else v = sm[L::LOSSJ + (k - 72 - kBetas - 3) * S + s];
+            P.out_packed[(size_t)b * kPacked + k] = v;
+        }
+    }
+}
+
 template <int S, class L = TileLayout<S>>
 SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm) {
     // per-iteration Adam scalars, computed in float64 like torch does on the host
@@ -323,27 +393,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
             ph_gemm_and_chain_backward<S, L>(M, sm);
             PHASE_MARK(10);
             const AdamScalars sc = (it < kMaxIters) ? adam_tab[it] : adam_scalars(P, it);
-            FOR_ITEMS(itj, kJoints * S) {
-                const int s = itj % S, j = itj / S;
-                float g[9], d[3];
-                rotation_grad<S, L>(sm, j, s, g);
-                rodrigues_bwd(sm[L::POSE + (3 * j + 0) * S + s], sm[L::POSE + (3 * j + 1) * S + s],
-                              sm[L::POSE + (3 * j + 2) * S + s], g, d);
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const int k = 3 * j + a;
-                    if (j > 0) d[a] += sm[L::GPR + (k - 3) * S + s];
-                    sm[L::POSE + k * S + s] = adam_update(sm[L::POSE + k * S + s], d[a], sm[L::ADM + k * S + s],
-                                                          sm[L::ADV + k * S + s], P.adam_c, sc);
-                }
-            }
-            FOR_ITEMS(itb, kBetas * S) {
-                const int s = itb % S, l = itb / S;
-                const float beta = sm[L::BETA + l * S + s];
-                const float g = beta_grad<S, L>(C, sm, l, s) + 2.f * kShapePriorW2 * beta;
-                sm[L::BETA + l * S + s] = adam_update(beta, g, sm[L::ADM + (72 + l) * S + s], sm[L::ADV + (72 + l) * S + s],
-                                                      P.adam_c, sc);
-            }
+            tile_adam_step<S, L>(C, P, sm, sc);
             TILE_SYNC();
             PHASE_MARK(11);
         }
@@ -351,43 +401,7 @@ SB_HD void fit_tile(const ModelView& M, const FitParams& P, int first, float* sm
 
     // ---- final forward: joints, per-joint reprojection loss, A and x for the vertex kernel --------
     tile_forward<S, L>(M, C, sm, true, false);
-    FOR_ITEMS(it, S * 147) {
-        const int s = it / 147, k = it % 147, b = first + s;
-        if (P.out_joints && b < P.batch) P.out_joints[(size_t)b * 147 + k] = sm[L::OUTJ + k * S + s];
-    }
-    tile_write_vertex_operands<S, L>(sm, first, P.batch, P.tc);
-    TILE_SYNC();
-    ph_reprojection<S, L>(sm, P.focal, kSigma2, false);
-    TILE_SYNC();
-    FOR_ITEMS(it, S * kOut) {
-        const int s = it / kOut, o = it % kOut, b = first + s;
-        if (b < P.batch) P.out_reproj[(size_t)b * kOut + o] = sm[L::LOSSJ + o * S + s];
-    }
-    FOR_ITEMS(it, S * 72) {
-        const int s = it / 72, k = it % 72, b = first + s;
-        if (P.out_pose && b < P.batch) P.out_pose[(size_t)b * 72 + k] = sm[L::POSE + k * S + s];
-    }
-    FOR_ITEMS(it, S * kBetas) {
-        const int s = it / kBetas, k = it % kBetas, b = first + s;
-        if (P.out_betas && b < P.batch) P.out_betas[(size_t)b * kBetas + k] = sm[L::BETA + k * S + s];
-    }
-    FOR_ITEMS(it, S * 3) {
-        const int s = it / 3, k = it % 3, b = first + s;
-        if (P.out_cam && b < P.batch) P.out_cam[(size_t)b * 3 + k] = sm[L::CAM + k * S + s];
-    }
-    if (P.out_packed) {
-        constexpr int kPacked = 72 + kBetas + 3 + kOut;
-        FOR_ITEMS(it, S * kPacked) {
-            const int s = it / kPacked, k = it % kPacked, b = first + s;
-            if (b >= P.batch) continue;
-            float v;
-            if (k < 72) v = sm[L::POSE + k * S + s];
-            else if (k < 72 + kBetas) v = sm[L::BETA + (k - 72) * S + s];
-            else if (k < 72 + kBetas + 3) v = sm[L::CAM + (k - 72 - kBetas) * S + s];
-            else v = sm[L::LOSSJ + (k - 72 - kBetas - 3) * S + s];
-            P.out_packed[(size_t)b * kPacked + k] = v;
-        }
-    }
+    tile_write_outputs<S, L>(P, first, sm);
 }
 
 // --------------------------------------------------------------------------------------------------

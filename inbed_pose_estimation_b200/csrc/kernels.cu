@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include "fit_driver.cuh"
 #include "fit_pair.cuh"
+#include "fit_split.cuh"
 #include "launch.h"
 
 namespace smplb200 {
@@ -35,6 +36,15 @@ __global__ void __launch_bounds__(kFitThreads, 1) smplify_fit_mixed_kernel(const
     const int blk = blockIdx.x;                                  // block-uniform branch
     if (blk < n_a) fit_tile<SA>(M, P, blk * SA, sm);
     else fit_tile<SB>(M, P, n_a * SA + (blk - n_a) * SB, sm);
+}
+
+// Small batches: a cluster of C CTAs per 4-sample tile, the three per-iteration GEMMs split by output rows (fit_split.cuh).
+// The cluster size is a launch attribute (cudaLaunchKernelEx).
+template <int C>
+__global__ void __launch_bounds__(kFitThreads, 1) smplify_fit_split_kernel(const __grid_constant__ ModelView M,
+                                                                           const __grid_constant__ FitParams P) {
+    extern __shared__ __align__(16) float sm[];
+    fit_split_tile<C>(M, P, (int)(blockIdx.x / C) * kSplitS, sm);
 }
 
 // Pairs of CTAs (2-CTA clusters) that share their GEMMs on the tensor cores (fit_pair.cuh): pairs [0, n_a) fit 2 x SA samples,
@@ -168,6 +178,35 @@ static cudaError_t launch_fit_pairs(const ModelView& M, const FitParams& P, int 
     return cudaGetLastError();
 }
 
+// Cluster size of the split kernel for a batch: the largest of 8 / 4 / 2 CTAs per 4-sample tile that fits the chip in one wave;
+// 0 = the batch is too large for it (the 4- / 8- / 12-sample tiles take over).
+int plan_fit_split(int batch, int sms) {
+    const int tiles = (batch + kSplitS - 1) / kSplitS;
+    for (int c = 8; c >= 2; c /= 2)
+        if (tiles * c <= sms) return c;
+    return 0;
+}
+
+template <int C>
+static cudaError_t launch_fit_split(const ModelView& M, const FitParams& P, cudaStream_t stream) {
+    const size_t smem = (size_t)SplitLayout::SMEM_FLOATS * sizeof(float);
+    cudaError_t e = opt_in_smem(smplify_fit_split_kernel<C>, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((P.batch + kSplitS - 1) / kSplitS * C));
+    cfg.blockDim = dim3(kFitThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, smplify_fit_split_kernel<C>, M, P);
+}
+
 // Batches from this size on run on the pair kernel (tensor-core GEMMs shared by two CTAs); smaller ones on the 4- / 8-sample
 // tiles of the CUDA-core kernel, which fill more SMs.
 constexpr int kPairMinBatch = 1024;
@@ -185,6 +224,12 @@ cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stre
     if (P.batch <= 0) return cudaSuccess;
     const int variant = fit_variant();
     if (fit_uses_pairs(P.batch, P.num_iters) && M.pg_fwd != nullptr) return launch_fit_pairs(M, P, device_sm_count(), stream);
+    if ((variant == 0 || variant == 12) && P.num_iters > 0) {
+        const int c = plan_fit_split(P.batch, device_sm_count());
+        if (c == 8) return launch_fit_split<8>(M, P, stream);
+        if (c == 4) return launch_fit_split<4>(M, P, stream);
+        if (c == 2) return launch_fit_split<2>(M, P, stream);
+    }
     if (variant == 1) return launch_fit_variant<8, 192, 2>(M, P, stream);
     if (variant == 2) return launch_fit_variant<8, 256, 2>(M, P, stream);
     if (variant == 3) return launch_fit_variant<16, 384, 1>(M, P, stream);

@@ -244,6 +244,11 @@ void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_sma
  * uses it for `batch` (then n16 / n12 = the numbers of 2 x 16- and 2 x 12-sample pairs on `sms` SMs), else 0 (the tile plan
  * above applies).  Pure host arithmetic. */
 int smplb200_fit_pair_plan(int batch, int sms, int* n16, int* n12);
+/* Small batches (the reference trains with --batch_size 32, README.md:33-35; SMPLify call at train/trainer.py:709-715): a
+ * cluster of 8, 4 or 2 CTAs fits each 4-sample tile, the per-iteration GEMMs split by output rows over the cluster
+ * (csrc/fit_split.cuh).  Returns the cluster size smplb200_smplify_fit uses for `batch` on a device with `sms` SMs, 0 when the
+ * batch is too large for it (more than sms / 2 tiles). */
+int smplb200_fit_split_plan(int batch, int sms);
 
 /* Number of this library's kernel launches issued by the process (any thread: torch autograd runs backward calls on
  * its own threads) since the last reset; reset != 0 returns the count and clears it (bench.py reports it as gpu_launches). */

@@ -49,13 +49,14 @@ def main():
     ap.add_argument('--seed', type=int, default=5)
     ap.add_argument('--out', default=None)
     ap.add_argument('--time', action='store_true')
+    ap.add_argument('--variant', default='10', help="SMPLB200_FIT_VARIANT of the second run: 10 = pair kernel, 12 = small-batch cluster kernel")
     a = ap.parse_args()
     if a.out:
         run_one(a)
         return
     tmp = tempfile.mkdtemp()
     res = {}
-    for name, variant in (('tile', '11'), ('pair', '10')):
+    for name, variant in (('tile', '11'), ('pair', a.variant)):
         out = os.path.join(tmp, name + '.npz')
         env = dict(os.environ, SMPLB200_FIT_VARIANT=variant)
         cmd = [sys.executable, os.path.abspath(__file__), '--batch', str(a.batch), '--iters', str(a.iters), '--seed', str(a.seed), '--out', out]
@@ -67,7 +68,7 @@ def main():
             return 1
         res[name] = np.load(out)
     t, p = res['tile'], res['pair']
-    print('batch %d, %d + %d iterations; tile kernel %.3f ms, pair kernel %.3f ms' % (a.batch, a.iters, a.iters, float(t['ms']), float(p['ms'])))
+    print('batch %d, %d + %d iterations; tile kernel %.3f ms, variant-%s kernel %.3f ms' % (a.batch, a.iters, a.iters, float(t['ms']), a.variant, float(p['ms'])))
     tr_t, tr_p = t['trace'], p['trace']
     rel = np.abs(tr_p - tr_t) / np.maximum(np.abs(tr_t), 1e-30)
     for i in range(tr_t.shape[0]):

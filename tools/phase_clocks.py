@@ -16,7 +16,7 @@ NAMES = ['prior GEMM', 'prior select + angle/shape priors', 'Rodrigues + pose fe
 
 if sys.argv[1] == 'build':
     from inbed_pose_estimation_b200 import _native
-    print(_native.build(force=True, extra_flags=['-DSMPLB200_PHASE_CLOCKS'], out=OUT))
+    print(_native.build(force=True, extra_flags=['-DSMPLB200_PHASE_CLOCKS'] + sys.argv[2:], out=OUT))
 else:
     os.environ['SMPLB200_LIB'] = OUT
     import argparse
@@ -27,6 +27,7 @@ else:
     ap.add_argument('--batch', type=int, default=4096)
     ap.add_argument('--iters', type=int, default=100)
     ap.add_argument('--pair', action='store_true', help='slot names of the pair kernel (fit_pair.cuh)')
+    ap.add_argument('--split', action='store_true', help='slot names of the small-batch cluster kernel (fit_split.cuh)')
     a = ap.parse_args()
     lib = _native.lib()
     fitter = synthetic.build_smplify('cuda', num_iters=a.iters, seed=0)
@@ -38,7 +39,16 @@ else:
         fitter(args[0], args[1], args[2], args[3], args[4].clone())
         torch.cuda.synchronize()
     lib.smplb200_debug_phase_clocks(buf, 0)
-    if a.pair:
+    if a.split:
+        names = ['pose features + rest joints', 'prior + forward GEMM rows (thread 0), reduce, broadcast', 'cluster barrier (incl. waiting for the chain warp / peers)',
+                 'prior select + 49 output joints', 'projection + GMoF (+ trace)', 'joint backward', 'picked-vertex backward',
+                 'backward GEMM rows, reduce, broadcast', 'cluster barrier', 'landing copy + Rodrigues backward + Adam',
+                 '  [beside the forward GEMMs] chain forward sweep (first chain thread)', '  [beside the backward GEMM] chain backward sweep']
+        tot = sum(buf[i] for i in range(10))
+        print('cluster kernel, CTA 0: %.0f cycles per stage-2 iteration (slots 0-2 include the 2 extra forward calls)' % (tot / a.iters))
+        for i, n in enumerate(names):
+            print('%-75s %9.0f clk/iter' % (n, buf[i] / (a.iters + 2 if i < 3 or i == 10 else a.iters)))
+    elif a.pair:
         names = {0: 'pose features + rest joints + B operands', 1: 'cluster barrier before the forward call', 2: 'forward call: generator warp 0 busy',
                  3: 'forward call: wait for the end barrier (gen warp 0)', 4: '49 output joints', 5: 'projection + GMoF', 6: 'joint backward',
                  7: 'picked-vertex backward', 8: 'cluster barrier before the backward call', 9: 'backward call: generator warp 0 busy',
