@@ -75,6 +75,22 @@ def test_fit_tile_plan_covers_every_batch_in_the_fewest_waves():
     assert _native.fit_tile_plan(0, sms) == (0, 0, 0)
 
 
+def test_fit_split_plan_cluster_sizes():
+    """smplb200_fit_split_plan: small batches run as clusters of 8 / 4 / 2 CTAs per 4-sample tile, the largest size whose
+    clusters all fit the chip at once; beyond sms / 2 tiles the tile kernels take over (no GPU: host arithmetic only)."""
+    sms = 148
+    for batch in range(1, 700):
+        c = _native.fit_split_plan(batch, sms)
+        tiles = (batch + 3) // 4
+        assert c in (0, 2, 4, 8)
+        if c:
+            assert tiles * c <= sms and (c == 8 or tiles * 2 * c > sms)
+        else:
+            assert tiles * 2 > sms
+    assert [_native.fit_split_plan(b, sms) for b in (1, 32, 72, 73, 148, 149, 256, 296, 297, 4096)] == [8, 8, 8, 4, 4, 2, 2, 2, 0, 0]
+    assert _native.fit_split_plan(0, sms) == 0 and _native.fit_split_plan(32, 1) == 0
+
+
 def test_product_never_touches_the_oracle():
     """oracle/ is test infrastructure: no file of the package (Python or CUDA/C++) may import, include or open it."""
     pkg = os.path.join(ROOT, 'inbed_pose_estimation_b200')

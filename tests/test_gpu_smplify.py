@@ -1,12 +1,14 @@
 """GPU parity of the fused SMPLify fit (through the C ABI) against the oracle and the
 reference-generated golden vectors.  Tolerances are BASELINE.json's: fitted parameters,
 joints and vertices within 1e-4 absolute, per-iteration losses within 1e-5 relative (fp32)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from conftest import golden
-from inbed_pose_estimation_b200 import constants as C, synthetic
+from inbed_pose_estimation_b200 import _native, constants as C, synthetic
 
 pytestmark = pytest.mark.gpu
 
@@ -60,6 +62,40 @@ def test_fit_matches_oracle_batch32(fitter, oracle_fp32):
     np.testing.assert_allclose(cam.cpu().numpy(), co.detach().numpy(), atol=1e-4)
     np.testing.assert_allclose(j.cpu().numpy(), jo.numpy(), atol=1e-4)
     np.testing.assert_allclose(v.cpu().numpy(), vo.numpy(), atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,cluster', [(30, 8), (101, 4), (203, 2)])
+def test_small_batch_cluster_kernel_matches_oracle(fitter, oracle_fp32, B, cluster):
+    """Small batches (the reference's --batch_size 32, README.md:33-35) run on clusters of 8 / 4 / 2 CTAs per 4-sample tile
+    (csrc/fit_split.cuh): ragged batches on every cluster size against the fp32 oracle, per-sample loss of every iteration."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if _native.fit_split_plan(B, sms) != cluster:
+        pytest.skip('cluster size %d is not what this device (%d SMs) plans for batch %d' % (cluster, sms, B))
+    inp = synthetic.make_fit_inputs(B, seed=300 + B)
+    rows = np.unique(np.concatenate([np.arange(4), np.arange(B - 6, B), np.random.RandomState(B).choice(B, 6, replace=False)]))
+    from test_gpu_parity_r2 import _assert_fit_rows, _oracle_rows
+    ref, ref_trace = _oracle_rows(oracle_fp32, inp, rows)
+    out = fitter(*_cuda(inp), return_loss_trace=True)
+    _assert_fit_rows(out, fitter.last_loss_trace.cpu().numpy(), rows, ref, ref_trace, 'cluster kernel, batch %d' % B, inp=inp)
+
+
+@pytest.mark.gpu
+def test_small_batch_cluster_kernel_agrees_with_the_tile_kernel():
+    """The same batch through the cluster kernel and through the 4-sample tile kernel (SMPLB200_FIT_VARIANT is read once per
+    process, hence tools/pair_debug.py's two child processes).  The two sum the GEMMs' reduction dimension in different
+    slices, so they agree to fp32 rounding carried through 200 Adam steps, not bit for bit."""
+    import subprocess, sys, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'pair_debug.py'), '--batch', '42', '--iters', '100', '--variant', '12'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert r.returncode == 0 and 'FAILED' not in r.stdout, r.stdout[-2000:]
+    diffs = dict(re.findall(r'^\s+(pose|betas|cam|joints|verts)\s+max abs diff ([0-9.e+-]+)', r.stdout, flags=re.M))
+    assert set(diffs) == {'pose', 'betas', 'cam', 'joints', 'verts'}, r.stdout[-2000:]
+    for k, v in diffs.items():
+        assert float(v) <= 2e-4, (k, v)
+    rel = [float(x) for x in re.findall(r'max rel loss diff ([0-9.e+-]+)', r.stdout)]
+    assert rel and max(rel) <= 3e-5 and 'NON-FINITE' not in r.stdout, r.stdout[-2000:]
 
 
 def test_fitting_loss_matches_golden(fitter):
