@@ -439,6 +439,29 @@ def run_ours(a):
         del fits_l, cam_l, cen_l, kp_l, packed_l, bulk
         torch.cuda.empty_cache()
 
+    # ---- BASELINE configs 2 and 3: the reference's own operating points (--batch_size 32; batch 256), device-timed ----------
+    small = None
+    if rank == 0 and world == 1 and not a.no_small:
+        small = {'note': 'SMPLify.__call__ 100+100 on a resident batch, median of 7 calls after 3 warm-ups, L2 flushed between calls; '
+                         'clusters of `cluster_size` CTAs per 4-sample tile (csrc/fit_split.cuh)', 'rows': []}
+        sms_here = torch.cuda.get_device_properties(dev).multi_processor_count
+        for b in (32, 256):
+            si = synthetic.make_fit_inputs(b, seed=9000 + b)
+            sa = [torch.from_numpy(si[k]).to(dev) for k in ('pose', 'betas', 'cam_t', 'center', 'keypoints')]
+            ms_s = []
+            for i in range(10):
+                flush.zero_()
+                kp = sa[4].clone()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fitter(sa[0], sa[1], sa[2], sa[3], kp)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms_s.append(e0.elapsed_time(e1))
+            small['rows'].append({'batch': b, 'ms': float(np.median(ms_s)), 'fits_per_sec': b / float(np.median(ms_s)) * 1e3,
+                                  'cluster_size': _native.fit_split_plan(b)})
+
     cpu = gpu_ref = lbs = None
     tf32_peak = None
     if rank == 0 and world == 1:
@@ -551,6 +574,8 @@ def run_ours(a):
             line['lbs'] = lbs
         if config4 is not None:
             line['config4'] = config4
+        if small is not None:
+            line['small_batch'] = small
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -568,6 +593,7 @@ def main():
     ap.add_argument('--no-gpu-reference', action='store_true', help='skip the eager-PyTorch-on-GPU denominator (about 40 s)')
     ap.add_argument('--no-lbs', action='store_true', help='skip the BASELINE config 5 rows')
     ap.add_argument('--no-config4', action='store_true', help='skip the 65 536-sample bulk refit')
+    ap.add_argument('--no-small', action='store_true', help='skip the batch-32 / batch-256 rows (BASELINE configs 2, 3)')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

@@ -263,8 +263,9 @@ def fit_tile_plan(batch, sms=148):
     return a.value, b.value, c.value
 
 
-def fit_split_plan(batch, sms=148):
-    """CTAs per 4-sample tile of the small-batch cluster kernel for this batch (8 / 4 / 2), 0 = the tile kernels run it."""
+def fit_split_plan(batch, sms=0):
+    """CTAs per 4-sample tile of the small-batch cluster kernel for this batch (8 / 4 / 2), 0 = the tile kernels run it.
+    sms = 0: what the launch uses on the current CUDA device (cluster occupancy); sms > 0: by SM count alone (upper bound)."""
     return int(lib().smplb200_fit_split_plan(int(batch), int(sms)))
 
 

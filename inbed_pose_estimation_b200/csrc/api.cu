@@ -87,7 +87,11 @@ extern "C" int smplb200_fit_pair_plan(int batch, int sms, int* n16, int* n12) {
     if (n12) *n12 = b;
     return pairs;
 }
-extern "C" int smplb200_fit_split_plan(int batch, int sms) { return (batch > 0 && sms > 1) ? plan_fit_split(batch, sms) : 0; }
+extern "C" int smplb200_fit_split_plan(int batch, int sms) {
+    if (batch <= 0) return 0;
+    if (sms <= 0) return plan_fit_split_device(batch);            // the current device's cluster occupancy: what the launch uses
+    return sms > 1 ? plan_fit_split(batch, sms) : 0;
+}
 extern "C" const char* smplb200_last_error(void) { return g_error.c_str(); }
 #if defined(SMPLB200_PHASE_CLOCKS)
 // profiling builds only (tools/phase_clocks.py): read / reset the stage-2 phase cycle counters

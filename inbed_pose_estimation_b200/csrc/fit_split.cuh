@@ -10,7 +10,7 @@
 //
 //   pose features, rest joints                                                            all CTAs, redundantly
 //   prior quadratic forms + folded GEMM forward: own rows -> Pd / Q of every CTA           split     || chain forward sweep (last 1-2 warps)
-//   -- cluster barrier --
+//   -- cluster barrier (the chain warps arrive before their sweep; the prior selection runs beside its tail) --
 //   prior selection, 49 output joints, projection + GMoF, joint / picked-vertex backward   all CTAs, redundantly
 //   folded GEMM backward: own rows of dL/dx -> landing rows of every CTA                   split     || chain backward sweep
 //   -- cluster barrier --
@@ -87,6 +87,9 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// the two halves on their own (whole warps): a warp that stores nothing into its peers arrives first and works on
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 template <int NT>
 __device__ __forceinline__ void gemm_threads_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
@@ -299,24 +302,34 @@ __device__ __forceinline__ void split_backward_gemm(const ModelView& M, float* s
         split::broadcast4<C>(sm, L::DXL + ((int)rank * PL::BQ * 4 + col) * S, split::sum_slices<PL::BS>(scr, PL::BQ * 4, col));
 }
 
+// Forward through the folded model for the tile's current parameters, up to (not including) the 49 output joints.  The chain
+// warps arrive at the cluster barrier BEFORE their sweep (they store nothing into the peers); the GEMM threads, once the
+// cluster's rows have landed, run the prior selection while the sweep - the longer of the two jobs - is still finishing.
 template <int C, class L>
-__device__ __forceinline__ void split_forward(const ModelView& M, const SmallConsts& Cn, float* sm, uint32_t rank, bool root_identity) {
+__device__ __forceinline__ void split_forward(const ModelView& M, const SmallConsts& Cn, float* sm, uint32_t rank, bool root_identity,
+                                              bool with_prior) {
     constexpr int S = kSplitS;
+    using PL = SplitPlan<C>;
     PHASE_BEGIN();
     ph_pose_features<S, L>(sm, true, root_identity);
     ph_rest_joints<S, L>(Cn, sm);
     TILE_SYNC();
     PHASE_MARK(0);
-    using PL = SplitPlan<C>;
     if ((int)threadIdx.x >= PL::GT) {
         SPLIT_CLK_BEGIN();
+        split::cluster_arrive();
         ph_chain_forward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GT, 32 * PL::CW, PL::CW == 1 ? 1 : 2});
         SPLIT_CLK_END(10, PL::GT);
+        split::cluster_wait();
     } else {
         split_forward_gemms<C, L>(M, Cn, sm, rank);
+        PHASE_MARK(1);
+        split::cluster_sync();
+        PHASE_MARK(12);
+        if (with_prior) ph_prior_select<S, L>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, Grp{(int)threadIdx.x, PL::GT, 3});
+        PHASE_MARK(13);
     }
-    PHASE_MARK(1);
-    split::cluster_sync();
+    TILE_SYNC();
 }
 
 // the whole fit of one 4-sample tile by a cluster of C CTAs of kFitThreads threads; `first` = first sample of the tile
@@ -358,7 +371,7 @@ __device__ void fit_split_tile(const ModelView& M, const FitParams& Pin, int fir
 
     if (P.num_iters > 0) {
         // ---- stage 1: global orientation + camera translation (every CTA, redundantly) ---------
-        split_forward<C, L>(M, Cn, sm, rank, /*root_identity=*/true);
+        split_forward<C, L>(M, Cn, sm, rank, /*root_identity=*/true, false);
         ph_output_joints<S, L>(M, Cn, sm);
         TILE_SYNC();
         stage1_camera<S, L>(M, P, first, sm);
@@ -370,9 +383,8 @@ __device__ void fit_split_tile(const ModelView& M, const FitParams& Pin, int fir
         // ---- stage 2 ---------------------------------------------------------------------------
         PHASE_BEGIN();
         for (int it = 0; it < P.num_iters; ++it) {
-            split_forward<C, L>(M, Cn, sm, rank, false);
+            split_forward<C, L>(M, Cn, sm, rank, false, true);
             PHASE_MARK(2);
-            ph_prior_select<S, L>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2);
             ph_output_joints<S, L>(M, Cn, sm);
             TILE_SYNC();
             PHASE_MARK(3);
@@ -417,7 +429,7 @@ __device__ void fit_split_tile(const ModelView& M, const FitParams& Pin, int fir
     }
 
     // ---- final forward; CTA 0 writes the results ------------------------------------------------
-    split_forward<C, L>(M, Cn, sm, rank, false);            // ends with the last cluster barrier: no store into a peer after it
+    split_forward<C, L>(M, Cn, sm, rank, false, false);     // holds the last cluster barrier: no store into a peer after it
     ph_output_joints<S, L>(M, Cn, sm);
     TILE_SYNC();
     if (rank == 0) tile_write_outputs<S, L>(P, first, sm);

@@ -39,6 +39,7 @@ SB_HD void grp_sync(const Grp& g) {
 #if defined(__CUDA_ARCH__)
     if (g.warp_only == 1) __syncwarp();
     else if (g.warp_only == 2) asm volatile("bar.sync 2, %0;" ::"r"(g.nt) : "memory");
+    else if (g.warp_only == 3) asm volatile("bar.sync 1, %0;" ::"r"(g.nt) : "memory");      // a second named group beside a `2` group
     else __syncthreads();
 #else
     (void)g;

@@ -178,32 +178,71 @@ static cudaError_t launch_fit_pairs(const ModelView& M, const FitParams& P, int 
     return cudaGetLastError();
 }
 
-// Cluster size of the split kernel for a batch: the largest of 8 / 4 / 2 CTAs per 4-sample tile that fits the chip in one wave;
-// 0 = the batch is too large for it (the 4- / 8- / 12-sample tiles take over).
-int plan_fit_split(int batch, int sms) {
+// Cluster size of the split kernel for a batch: the largest of 8 / 4 / 2 CTAs per 4-sample tile whose clusters are all resident
+// at once; 0 = the batch is too large for it (the 4- / 8- / 12-sample tiles take over).  `capacity[i]` = clusters of 8 / 4 / 2
+// CTAs the device holds at a time.
+static int plan_fit_split_caps(int batch, const int capacity[3]) {
     const int tiles = (batch + kSplitS - 1) / kSplitS;
-    for (int c = 8; c >= 2; c /= 2)
-        if (tiles * c <= sms) return c;
+    for (int i = 0, c = 8; c >= 2; c /= 2, ++i)
+        if (tiles <= capacity[i]) return c;
     return 0;
+}
+// ... by SM count alone (an upper bound: sms / C clusters)
+int plan_fit_split(int batch, int sms) {
+    const int cap[3] = {sms / 8, sms / 4, sms / 2};
+    return plan_fit_split_caps(batch, cap);
 }
 
 template <int C>
-static cudaError_t launch_fit_split(const ModelView& M, const FitParams& P, cudaStream_t stream) {
-    const size_t smem = (size_t)SplitLayout::SMEM_FLOATS * sizeof(float);
-    cudaError_t e = opt_in_smem(smplify_fit_split_kernel<C>, smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((P.batch + kSplitS - 1) / kSplitS * C));
+static void fill_split_launch(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int clusters, cudaStream_t stream) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)(clusters * C));
     cfg.blockDim = dim3(kFitThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = (size_t)SplitLayout::SMEM_FLOATS * sizeof(float);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+}
+
+// clusters of C CTAs of the split kernel the CURRENT device holds at a time (one CTA per SM; a cluster lives inside one GPC, so
+// this is less than sms / C: 16 clusters of 8 would need 128 of the 148 SMs in whole groups of 8 per GPC - measured on B200: a
+// batch of 64 planned by SM count alone ran as two waves, 3.67 instead of 1.88 ms)
+template <int C>
+static int split_cluster_capacity() {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    fill_split_launch<C>(cfg, attr, 1, nullptr);
+    int n = 0;
+    if (opt_in_smem(smplify_fit_split_kernel<C>, cfg.dynamicSmemBytes) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveClusters(&n, smplify_fit_split_kernel<C>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+// ... for the current device, cached per device index
+int plan_fit_split_device(int batch) {
+    static int cache[64][3];
+    static bool known[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    if (!known[dev]) {
+        cache[dev][0] = split_cluster_capacity<8>();
+        cache[dev][1] = split_cluster_capacity<4>();
+        cache[dev][2] = split_cluster_capacity<2>();
+        known[dev] = true;                               // benign race: every thread writes the same values
+    }
+    return plan_fit_split_caps(batch, cache[dev]);
+}
+
+template <int C>
+static cudaError_t launch_fit_split(const ModelView& M, const FitParams& P, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    fill_split_launch<C>(cfg, attr, (P.batch + kSplitS - 1) / kSplitS, stream);
+    cudaError_t e = opt_in_smem(smplify_fit_split_kernel<C>, cfg.dynamicSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&cfg, smplify_fit_split_kernel<C>, M, P);
 }
 
@@ -225,7 +264,7 @@ cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stre
     const int variant = fit_variant();
     if (fit_uses_pairs(P.batch, P.num_iters) && M.pg_fwd != nullptr) return launch_fit_pairs(M, P, device_sm_count(), stream);
     if ((variant == 0 || variant == 12) && P.num_iters > 0) {
-        const int c = plan_fit_split(P.batch, device_sm_count());
+        const int c = plan_fit_split_device(P.batch);
         if (c == 8) return launch_fit_split<8>(M, P, stream);
         if (c == 4) return launch_fit_split<4>(M, P, stream);
         if (c == 2) return launch_fit_split<2>(M, P, stream);

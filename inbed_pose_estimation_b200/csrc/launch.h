@@ -15,7 +15,8 @@ constexpr int kPoseThreads = 384;
 cudaError_t launch_fit(const ModelView& M, const FitParams& P, cudaStream_t stream);
 void plan_fit_tiles(int batch, int sms, int* n16, int* small, int* n_small);
 void plan_fit_pairs(int batch, int sms, int* n16, int* n12);
-int plan_fit_split(int batch, int sms);      // CTAs per 4-sample tile of the small-batch cluster kernel (8 / 4 / 2), 0 = not used
+int plan_fit_split(int batch, int sms);      // CTAs per 4-sample tile of the small-batch cluster kernel (8 / 4 / 2), 0 = not used: by SM count (upper bound)
+int plan_fit_split_device(int batch);        // ... by the cluster occupancy of the current device (what the launch uses)
 int fit_uses_pairs(int batch, int num_iters);      // 1 when launch_fit runs the batch on the pair kernel (tensor-core GEMMs)
 int device_sm_count();      // of the current device (cached per device index)
 cudaError_t launch_prior_terms(const ModelView& M, const PriorParams& P, cudaStream_t stream);

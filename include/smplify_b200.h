@@ -246,8 +246,10 @@ void smplb200_fit_tile_plan(int batch, int sms, int* n16, int* small, int* n_sma
 int smplb200_fit_pair_plan(int batch, int sms, int* n16, int* n12);
 /* Small batches (the reference trains with --batch_size 32, README.md:33-35; SMPLify call at train/trainer.py:709-715): a
  * cluster of 8, 4 or 2 CTAs fits each 4-sample tile, the per-iteration GEMMs split by output rows over the cluster
- * (csrc/fit_split.cuh).  Returns the cluster size smplb200_smplify_fit uses for `batch` on a device with `sms` SMs, 0 when the
- * batch is too large for it (more than sms / 2 tiles). */
+ * (csrc/fit_split.cuh).  Returns the cluster size for `batch`, 0 when the batch is too large for the cluster kernel.
+ * sms <= 0: the plan smplb200_smplify_fit uses on the CURRENT device - the largest cluster size whose clusters are all
+ * resident at once (cudaOccupancyMaxActiveClusters: clusters live inside one GPC, so fewer than sms / C fit); needs a GPU.
+ * sms > 0: the same arithmetic with sms / C clusters assumed resident (an upper bound; no GPU needed). */
 int smplb200_fit_split_plan(int batch, int sms);
 
 /* Number of this library's kernel launches issued by the process (any thread: torch autograd runs backward calls on

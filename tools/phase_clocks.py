@@ -40,14 +40,15 @@ else:
         torch.cuda.synchronize()
     lib.smplb200_debug_phase_clocks(buf, 0)
     if a.split:
-        names = ['pose features + rest joints', 'prior + forward GEMM rows (thread 0), reduce, broadcast', 'cluster barrier (incl. waiting for the chain warp / peers)',
-                 'prior select + 49 output joints', 'projection + GMoF (+ trace)', 'joint backward', 'picked-vertex backward',
+        names = ['pose features + rest joints', 'prior + forward GEMM rows (thread 0), reduce, broadcast', 'whole forward (slots 0, 1, 12, 13 + waiting for the chain sweep)',
+                 '49 output joints', 'projection + GMoF (+ trace)', 'joint backward', 'picked-vertex backward',
                  'backward GEMM rows, reduce, broadcast', 'cluster barrier', 'landing copy + Rodrigues backward + Adam',
-                 '  [beside the forward GEMMs] chain forward sweep (first chain thread)', '  [beside the backward GEMM] chain backward sweep']
+                 '  [beside the forward GEMMs] chain forward sweep (first chain thread)', '  [beside the backward GEMM] chain backward sweep',
+                 '  cluster barrier after the forward GEMMs (thread 0)', '  prior selection on the GEMM threads']
         tot = sum(buf[i] for i in range(10))
         print('cluster kernel, CTA 0: %.0f cycles per stage-2 iteration (slots 0-2 include the 2 extra forward calls)' % (tot / a.iters))
         for i, n in enumerate(names):
-            print('%-75s %9.0f clk/iter' % (n, buf[i] / (a.iters + 2 if i < 3 or i == 10 else a.iters)))
+            print('%-75s %9.0f clk/iter' % (n, buf[i] / (a.iters + 2 if i < 3 or i in (10, 12) else a.iters)))
     elif a.pair:
         names = {0: 'pose features + rest joints + B operands', 1: 'cluster barrier before the forward call', 2: 'forward call: generator warp 0 busy',
                  3: 'forward call: wait for the end barrier (gen warp 0)', 4: '49 output joints', 5: 'projection + GMoF', 6: 'joint backward',
