@@ -440,9 +440,9 @@ def run_ours(a):
         torch.cuda.empty_cache()
 
     # ---- BASELINE configs 2 and 3: the reference's own operating points (--batch_size 32; batch 256), device-timed ----------
-    small = None
+    small_rows = None
     if rank == 0 and world == 1 and not a.no_small:
-        small = {'note': 'SMPLify.__call__ 100+100 on a resident batch, median of 7 calls after 3 warm-ups, L2 flushed between calls; '
+        small_rows = {'note': 'SMPLify.__call__ 100+100 on a resident batch, median of 7 calls after 3 warm-ups, L2 flushed between calls; '
                          'clusters of `cluster_size` CTAs per 4-sample tile (csrc/fit_split.cuh)', 'rows': []}
         sms_here = torch.cuda.get_device_properties(dev).multi_processor_count
         for b in (32, 256):
@@ -459,7 +459,7 @@ def run_ours(a):
                 torch.cuda.synchronize()
                 if i >= 3:
                     ms_s.append(e0.elapsed_time(e1))
-            small['rows'].append({'batch': b, 'ms': float(np.median(ms_s)), 'fits_per_sec': b / float(np.median(ms_s)) * 1e3,
+            small_rows['rows'].append({'batch': b, 'ms': float(np.median(ms_s)), 'fits_per_sec': b / float(np.median(ms_s)) * 1e3,
                                   'cluster_size': _native.fit_split_plan(b)})
 
     cpu = gpu_ref = lbs = None
@@ -574,8 +574,8 @@ def run_ours(a):
             line['lbs'] = lbs
         if config4 is not None:
             line['config4'] = config4
-        if small is not None:
-            line['small_batch'] = small
+        if small_rows is not None:
+            line['small_batch'] = small_rows
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
