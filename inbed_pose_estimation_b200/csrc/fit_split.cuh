@@ -11,9 +11,9 @@
 //   pose features, rest joints                                                            all CTAs, redundantly
 //   prior quadratic forms + folded GEMM forward: own rows -> Pd / Q of every CTA           split     || chain forward sweep (last 1-2 warps)
 //   -- cluster barrier (the chain warps arrive before their sweep; the prior selection runs beside its tail) --
-//   prior selection, 49 output joints, projection + GMoF, joint / picked-vertex backward   all CTAs, redundantly
-//   folded GEMM backward: own rows of dL/dx -> landing rows of every CTA                   split     || chain backward sweep
-//   -- cluster barrier --
+//   prior selection, 49 output joints, projection + GMoF, joint backward                   all CTAs, redundantly
+//   picked-vertex backward, folded GEMM backward: own rows of dL/dx -> landing rows of every CTA    || chain backward sweep
+//   -- cluster barrier (again the chain warps arrive first) --
 //   Rodrigues backward + Adam                                                              all CTAs, redundantly
 //
 // Sums over the reduction slices are added in a fixed order (deterministic; not the order of the 4-sample tile kernel: the
@@ -326,7 +326,7 @@ __device__ __forceinline__ void split_forward(const ModelView& M, const SmallCon
         PHASE_MARK(1);
         split::cluster_sync();
         PHASE_MARK(12);
-        if (with_prior) ph_prior_select<S, L>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, Grp{(int)threadIdx.x, PL::GT, 3});
+        if (with_prior) ph_prior_select<S, L, 8>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, Grp{(int)threadIdx.x, PL::GT, 3});
         PHASE_MARK(13);
     }
     TILE_SYNC();
@@ -404,21 +404,27 @@ __device__ void fit_split_tile(const ModelView& M, const FitParams& Pin, int fir
             ph_joint_backward<S, L>(M, Cn, sm);
             TILE_SYNC();
             PHASE_MARK(5);
-            ph_pick_backward<S, L>(M, Cn, sm);
-            TILE_SYNC();
-            PHASE_MARK(6);
+            // the picked-vertex backward only adds dQ rows (it reads the source gradients and the transforms): the chain warps
+            // skip it and start their reverse sweep - the longest job of this half - on what the joint backward left
             using PL = SplitPlan<C>;
             if ((int)threadIdx.x >= PL::GT) {
                 SPLIT_CLK_BEGIN();
+                split::cluster_arrive();                           // nothing of the sweep goes to a peer
                 ph_chain_backward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GT, 32 * PL::CW, PL::CW == 1 ? 1 : 2});
                 SPLIT_CLK_END(11, PL::GT);
+                split::cluster_wait();
             } else {
+                static_assert(kPicks * S <= PL::GT, "one picked-vertex item per GEMM thread");
+                ph_pick_backward<S, L>(M, Cn, sm);                 // items < GT: the chain warps own none
+                split::gemm_threads_sync<PL::GT>();
+                PHASE_MARK(6);
                 split_backward_gemm<C, L>(M, sm, rank);
+                PHASE_MARK(7);
+                split::cluster_sync();
+                PHASE_MARK(8);
+                for (int i = (int)threadIdx.x; i < kXPad * S; i += PL::GT) sm[L::XT + i] = sm[L::DXL + i];      // beside the sweep's tail
             }
-            PHASE_MARK(7);
-            split::cluster_sync();
-            PHASE_MARK(8);
-            FOR_ITEMS(i, kXPad * S) sm[L::XT + i] = sm[L::DXL + i];
+            TILE_SYNC();
             ph_chain_backward_finish_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, grp_tile());
             TILE_SYNC();
             const AdamScalars sc = (it < kMaxIters) ? adam_tab[it] : adam_scalars(P, it);

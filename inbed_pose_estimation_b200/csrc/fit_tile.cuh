@@ -814,15 +814,38 @@ SB_HD_CALL void ph_prior_quadratic(const ModelView& M, const SmallConsts& C, flo
     }
 }
 
-template <int S, class L = TileLayout<S>>
+// QSPLIT > 1 (small tiles, where 8 S items leave most threads idle): every quadratic form is summed in QSPLIT runs of
+// consecutive terms by QSPLIT threads and the partial sums are added in run order (through the GPR rows, written last).
+template <int S, class L = TileLayout<S>, int QSPLIT = 1>
 SB_HD void ph_prior_select(const ModelView& M, const SmallConsts& C, float* sm, float prior_w2, float angle_w2, float shape_w2,
                            const Grp grp = grp_tile()) {
-    FOR_ITEMS_G(it, kGauss * S, grp) {
-        const int s = it % S, g = it / S;
-        float q = 0.f;
-        for (int i = 0; i < kPriorDim; ++i)
-            q += sm[L::pd(g, i, s)] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
-        sm[L::MISC + g * S + s] = 0.5f * q - C.lognll[g];
+    if constexpr (QSPLIT > 1) {
+        constexpr int RUN = (kPriorDim + QSPLIT - 1) / QSPLIT;
+        static_assert(QSPLIT * kGauss <= kPriorDim, "partial sums must fit in the GPR rows");
+        FOR_ITEMS_G(it, QSPLIT * kGauss * S, grp) {
+            const int s = it % S, g = (it / S) % kGauss, part = it / (kGauss * S);
+            const int i1 = (part + 1) * RUN < kPriorDim ? (part + 1) * RUN : kPriorDim;
+            float q = 0.f;
+            for (int i = part * RUN; i < i1; ++i)
+                q += sm[L::pd(g, i, s)] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
+            sm[L::GPR + (part * kGauss + g) * S + s] = q;
+        }
+        grp_sync(grp);
+        FOR_ITEMS_G(it, kGauss * S, grp) {
+            const int s = it % S, g = it / S;
+            float q = sm[L::GPR + g * S + s];
+#pragma unroll
+            for (int part = 1; part < QSPLIT; ++part) q += sm[L::GPR + (part * kGauss + g) * S + s];
+            sm[L::MISC + g * S + s] = 0.5f * q - C.lognll[g];
+        }
+    } else {
+        FOR_ITEMS_G(it, kGauss * S, grp) {
+            const int s = it % S, g = it / S;
+            float q = 0.f;
+            for (int i = 0; i < kPriorDim; ++i)
+                q += sm[L::pd(g, i, s)] * (sm[L::POSE + (3 + i) * S + s] - C.mu[g * kPriorPad + i]);
+            sm[L::MISC + g * S + s] = 0.5f * q - C.lognll[g];
+        }
     }
     grp_sync(grp);
     FOR_ITEMS_G(s, S, grp) {
