@@ -26,26 +26,29 @@ namespace smplb200 {
 constexpr int kSplitS = 4;                         // samples per cluster
 
 // Work split of the three GEMMs for a cluster of C CTAs: (output items per CTA) x (reduction slices) <= GT = 384 - 32 CW GEMM
-// threads, the last CW warps run the kinematic-chain sweeps beside them; every slice length is a multiple of 4, at least 8
+// threads, the last CW warps run the kinematic-chain sweeps beside them (per half of the iteration: GTF / CWF, GTB / CWB); every slice length is a multiple of 4, at least 8
 // (stream_gemm)
 template <int C> struct SplitPlan;
 template <> struct SplitPlan<8> {
     static constexpr int FQ = 22, FS = 14, FR = 16;      // forward: 22 column quads x 14 slices of 16 of the 224 x rows
     static constexpr int PI = 18, PS = 9, PR = 8;        // prior:   one component (18 column quads) x 9 slices of 8 of the 72 rows
     static constexpr int BQ = 7, BS = 44, BR = 16;       // backward: 7 column quads x 44 slices of 16 of the 704 dQ rows
-    static constexpr int CW = 2, GT = kFitTileThreads - 32 * CW;
+    static constexpr int CWF = 2, GTF = kFitTileThreads - 32 * CWF;     // chain warps / GEMM threads of the forward half
+    static constexpr int CWB = 2, GTB = kFitTileThreads - 32 * CWB;     // ... of the backward half
 };
 template <> struct SplitPlan<4> {
     static constexpr int FQ = 44, FS = 7, FR = 32;
     static constexpr int PI = 36, PS = 6, PR = 12;
     static constexpr int BQ = 14, BS = 22, BR = 32;
-    static constexpr int CW = 2, GT = kFitTileThreads - 32 * CW;
+    static constexpr int CWF = 2, GTF = kFitTileThreads - 32 * CWF;     // chain warps / GEMM threads of the forward half
+    static constexpr int CWB = 2, GTB = kFitTileThreads - 32 * CWB;     // ... of the backward half
 };
 template <> struct SplitPlan<2> {
     static constexpr int FQ = 88, FS = 4, FR = 56;
     static constexpr int PI = 72, PS = 3, PR = 24;
     static constexpr int BQ = 28, BS = 11, BR = 64;
-    static constexpr int CW = 1, GT = kFitTileThreads - 32 * CW;
+    static constexpr int CWF = 1, GTF = kFitTileThreads - 32 * CWF;     // 88 column quads x 4 slices need 352 GEMM threads
+    static constexpr int CWB = 2, GTB = kFitTileThreads - 32 * CWB;
 };
 
 // tile state of fit_tile.cuh (S = 4) + the regions the split needs
@@ -248,8 +251,8 @@ template <int C, class L>
 __device__ __forceinline__ void split_forward_gemms(const ModelView& M, const SmallConsts& Cn, float* sm, uint32_t rank) {
     using PL = SplitPlan<C>;
     constexpr int S = kSplitS, NQ4 = kQPad / 4, IQ = kPriorPad / 4;
-    static_assert(PL::FQ * C == NQ4 && PL::FS * PL::FR == kXPad && PL::FQ * PL::FS <= PL::GT, "forward split");
-    static_assert(PL::PI * C == kGauss * IQ && PL::PS * PL::PR == kPriorPad && PL::PI * PL::PS <= PL::GT, "prior split");
+    static_assert(PL::FQ * C == NQ4 && PL::FS * PL::FR == kXPad && PL::FQ * PL::FS <= PL::GTF, "forward split");
+    static_assert(PL::PI * C == kGauss * IQ && PL::PS * PL::PR == kPriorPad && PL::PI * PL::PS <= PL::GTF, "prior split");
     static_assert(PL::FS * PL::FQ * 16 <= 5632 && PL::PS * PL::PI * 16 <= 5184, "scratch sizes");
     const int t = (int)threadIdx.x;
     float* scr_p = sm + L::SCR_P;
@@ -269,15 +272,15 @@ __device__ __forceinline__ void split_forward_gemms(const ModelView& M, const Sm
         stream_gemm<PL::FR, NQ4, S>(acc, reinterpret_cast<const float4*>(M.Cf) + cq + (size_t)ks * PL::FR * NQ4, sm + L::XT + ks * PL::FR * S);
         split::store_partial(acc, scr_f, ks, PL::FQ * 4, 4 * ql);
     }
-    split::gemm_threads_sync<PL::GT>();
-    for (int col = t; col < PL::PI * 4; col += PL::GT) {
+    split::gemm_threads_sync<PL::GTF>();
+    for (int col = t; col < PL::PI * 4; col += PL::GTF) {
         const int gi4 = (int)rank * PL::PI * 4 + col;                                 // = g * 72 + i (18 quads of 4 per component)
         float4 v = split::sum_slices<PL::PS>(scr_p, PL::PI * 4, col);
         const float pm = Cn.pmean[gi4];
         v.x -= pm; v.y -= pm; v.z -= pm; v.w -= pm;
         split::broadcast4<C>(sm, L::PD + gi4 * S, v);
     }
-    for (int col = t; col < PL::FQ * 4; col += PL::GT)
+    for (int col = t; col < PL::FQ * 4; col += PL::GTF)
         split::broadcast4<C>(sm, L::q((int)rank * PL::FQ * 4 + col, 0), split::sum_slices<PL::FS>(scr_f, PL::FQ * 4, col));
 }
 
@@ -286,7 +289,7 @@ template <int C, class L>
 __device__ __forceinline__ void split_backward_gemm(const ModelView& M, float* sm, uint32_t rank) {
     using PL = SplitPlan<C>;
     constexpr int S = kSplitS, MQ = kXPad / 4;
-    static_assert(PL::BQ * C == MQ && PL::BS * PL::BR == kQPad && PL::BQ * PL::BS <= PL::GT, "backward split");
+    static_assert(PL::BQ * C == MQ && PL::BS * PL::BR == kQPad && PL::BQ * PL::BS <= PL::GTB, "backward split");
     static_assert(PL::BS * PL::BQ * 16 <= 5632, "scratch size");
     const int t = (int)threadIdx.x;
     float* scr = sm + L::SCR_F;
@@ -297,8 +300,8 @@ __device__ __forceinline__ void split_backward_gemm(const ModelView& M, float* s
         stream_gemm<PL::BR, MQ, L::LDQ>(acc, reinterpret_cast<const float4*>(M.CfT) + (size_t)ns * PL::BR * MQ + mq, sm + L::QT + ns * PL::BR * L::LDQ);
         split::store_partial(acc, scr, ns, PL::BQ * 4, 4 * ml);
     }
-    split::gemm_threads_sync<PL::GT>();
-    for (int col = t; col < PL::BQ * 4; col += PL::GT)
+    split::gemm_threads_sync<PL::GTB>();
+    for (int col = t; col < PL::BQ * 4; col += PL::GTB)
         split::broadcast4<C>(sm, L::DXL + ((int)rank * PL::BQ * 4 + col) * S, split::sum_slices<PL::BS>(scr, PL::BQ * 4, col));
 }
 
@@ -315,18 +318,18 @@ __device__ __forceinline__ void split_forward(const ModelView& M, const SmallCon
     ph_rest_joints<S, L>(Cn, sm);
     TILE_SYNC();
     PHASE_MARK(0);
-    if ((int)threadIdx.x >= PL::GT) {
+    if ((int)threadIdx.x >= PL::GTF) {
         SPLIT_CLK_BEGIN();
         split::cluster_arrive();
-        ph_chain_forward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GT, 32 * PL::CW, PL::CW == 1 ? 1 : 2});
-        SPLIT_CLK_END(10, PL::GT);
+        ph_chain_forward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GTF, 32 * PL::CWF, PL::CWF == 1 ? 1 : 2});
+        SPLIT_CLK_END(10, PL::GTF);
         split::cluster_wait();
     } else {
         split_forward_gemms<C, L>(M, Cn, sm, rank);
         PHASE_MARK(1);
         split::cluster_sync();
         PHASE_MARK(12);
-        if (with_prior) ph_prior_select<S, L, 8>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, Grp{(int)threadIdx.x, PL::GT, 3});
+        if (with_prior) ph_prior_select<S, L, 8>(M, Cn, sm, kPosePriorW2, kAnglePriorW2, kShapePriorW2, Grp{(int)threadIdx.x, PL::GTF, 3});
         PHASE_MARK(13);
     }
     TILE_SYNC();
@@ -407,22 +410,22 @@ __device__ void fit_split_tile(const ModelView& M, const FitParams& Pin, int fir
             // the picked-vertex backward only adds dQ rows (it reads the source gradients and the transforms): the chain warps
             // skip it and start their reverse sweep - the longest job of this half - on what the joint backward left
             using PL = SplitPlan<C>;
-            if ((int)threadIdx.x >= PL::GT) {
+            if ((int)threadIdx.x >= PL::GTB) {
                 SPLIT_CLK_BEGIN();
                 split::cluster_arrive();                           // nothing of the sweep goes to a peer
-                ph_chain_backward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GT, 32 * PL::CW, PL::CW == 1 ? 1 : 2});
-                SPLIT_CLK_END(11, PL::GT);
+                ph_chain_backward_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, Grp{(int)threadIdx.x - PL::GTB, 32 * PL::CWB, PL::CWB == 1 ? 1 : 2});
+                SPLIT_CLK_END(11, PL::GTB);
                 split::cluster_wait();
             } else {
-                static_assert(kPicks * S <= PL::GT, "one picked-vertex item per GEMM thread");
+                static_assert(kPicks * S <= PL::GTB, "one picked-vertex item per GEMM thread");
                 ph_pick_backward<S, L>(M, Cn, sm);                 // items < GT: the chain warps own none
-                split::gemm_threads_sync<PL::GT>();
+                split::gemm_threads_sync<PL::GTB>();
                 PHASE_MARK(6);
                 split_backward_gemm<C, L>(M, sm, rank);
                 PHASE_MARK(7);
                 split::cluster_sync();
                 PHASE_MARK(8);
-                for (int i = (int)threadIdx.x; i < kXPad * S; i += PL::GT) sm[L::XT + i] = sm[L::DXL + i];      // beside the sweep's tail
+                for (int i = (int)threadIdx.x; i < kXPad * S; i += PL::GTB) sm[L::XT + i] = sm[L::DXL + i];      // beside the sweep's tail
             }
             TILE_SYNC();
             ph_chain_backward_finish_rows<S, L>(*reinterpret_cast<const ChainTree*>(sm + L::TREE), sm, grp_tile());
