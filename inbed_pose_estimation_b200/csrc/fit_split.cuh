@@ -152,74 +152,109 @@ __device__ __forceinline__ void stage_chain_tree(const ModelView& M, ChainTree* 
     if (threadIdx.x == 0) t->num_levels = M.num_levels;
 }
 
+// one row r of joint j's world transform (parent p, -1 = root) for sample s
+template <int S, class L>
+__device__ __forceinline__ void chain_forward_row(float* sm, int j, int p, int r, int s) {
+    float G[4];
+    const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s], Jz = sm[L::JR + (3 * j + 2) * S + s];
+    if (p < 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[c] = sm[L::RM + (j * 9 + r * 3 + c) * S + s];
+        G[3] = (r == 0) ? Jx : ((r == 1) ? Jy : Jz);
+    } else {
+        float Rl[9], Gp[4];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rl[e] = sm[L::RM + (j * 9 + e) * S + s];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Gp[e] = sm[L::GW + (p * 12 + r * 4 + e) * S + s];
+        const float dx = Jx - sm[L::JR + (3 * p + 0) * S + s], dy = Jy - sm[L::JR + (3 * p + 1) * S + s],
+                    dz = Jz - sm[L::JR + (3 * p + 2) * S + s];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) G[c] = Gp[0] * Rl[c] + Gp[1] * Rl[3 + c] + Gp[2] * Rl[6 + c];
+        G[3] = Gp[0] * dx + Gp[1] * dy + Gp[2] * dz + Gp[3];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sm[L::GW + (j * 12 + r * 4 + e) * S + s] = G[e];
+    sm[L::AT + (3 * j + r) * S + s] = G[3] - (G[0] * Jx + G[1] * Jy + G[2] * Jz);
+}
+
+// Level by level.  A thread's first item of the NEXT level (joint, parent: three dependent table look-ups that do not depend on
+// this level's results) is looked up before this level's arithmetic, so that it is off the level-to-level critical path.
 template <int S, class L>
 __device__ __forceinline__ void ph_chain_forward_rows(const ChainTree& M, float* sm, const Grp g) {
-    for (int lev = 0; lev < M.num_levels; ++lev) {
-        const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
-        FOR_ITEMS_G(it, cnt * 3 * S, g) {
-            const int s = it % S, r = (it / S) % 3, j = M.level_order[first + it / (3 * S)], p = M.parents[j];
-            float G[4];
-            const float Jx = sm[L::JR + (3 * j + 0) * S + s], Jy = sm[L::JR + (3 * j + 1) * S + s], Jz = sm[L::JR + (3 * j + 2) * S + s];
-            if (p < 0) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) G[c] = sm[L::RM + (j * 9 + r * 3 + c) * S + s];
-                G[3] = (r == 0) ? Jx : ((r == 1) ? Jy : Jz);
-            } else {
-                float Rl[9], Gp[4];
-#pragma unroll
-                for (int e = 0; e < 9; ++e) Rl[e] = sm[L::RM + (j * 9 + e) * S + s];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) Gp[e] = sm[L::GW + (p * 12 + r * 4 + e) * S + s];
-                const float dx = Jx - sm[L::JR + (3 * p + 0) * S + s], dy = Jy - sm[L::JR + (3 * p + 1) * S + s],
-                            dz = Jz - sm[L::JR + (3 * p + 2) * S + s];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) G[c] = Gp[0] * Rl[c] + Gp[1] * Rl[3 + c] + Gp[2] * Rl[6 + c];
-                G[3] = Gp[0] * dx + Gp[1] * dy + Gp[2] * dz + Gp[3];
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) sm[L::GW + (j * 12 + r * 4 + e) * S + s] = G[e];
-            sm[L::AT + (3 * j + r) * S + s] = G[3] - (G[0] * Jx + G[1] * Jy + G[2] * Jz);
+    const int levels = M.num_levels, s = g.tid % S, r = (g.tid / S) % 3, slot = g.tid / (3 * S);
+    int first = M.level_start[0], cnt = M.level_start[1] - first;
+    int j0 = -1, p0 = -1;
+    if (slot < cnt) { j0 = M.level_order[first + slot]; p0 = M.parents[j0]; }
+    for (int lev = 0; lev < levels; ++lev) {
+        int nfirst = 0, ncnt = 0, nj = -1, np = -1;
+        if (lev + 1 < levels) {
+            nfirst = M.level_start[lev + 1];
+            ncnt = M.level_start[lev + 2] - nfirst;
+            if (slot < ncnt) { nj = M.level_order[nfirst + slot]; np = M.parents[nj]; }
+        }
+        if (j0 >= 0) chain_forward_row<S, L>(sm, j0, p0, r, s);
+        for (int it = g.tid + g.nt; it < cnt * 3 * S; it += g.nt) {              // further passes of a wide level / a narrow group
+            const int j = M.level_order[first + it / (3 * S)];
+            chain_forward_row<S, L>(sm, j, M.parents[j], (it / S) % 3, it % S);
         }
         grp_sync(g);
+        first = nfirst; cnt = ncnt; j0 = nj; p0 = np;
     }
+}
+
+// row r of parent p's accumulated dL/dG and entry r of its rest-joint gradient, gathered from its children [c0, c1)
+template <int S, class L>
+__device__ __forceinline__ void chain_backward_row(const ChainTree& M, float* sm, int p, int c0, int c1, int r, int s) {
+    float dGp[4], Gp[3];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dGp[e] = sm[L::DG + (p * 12 + r * 4 + e) * S + s];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) Gp[k] = sm[L::GW + (p * 12 + k * 4 + r) * S + s];            // column r of G_p^R
+    float dJp = sm[L::DJ + (3 * p + r) * S + s];
+    const float Jpx = sm[L::JR + (3 * p + 0) * S + s], Jpy = sm[L::JR + (3 * p + 1) * S + s], Jpz = sm[L::JR + (3 * p + 2) * S + s];
+    for (int ci = c0; ci < c1; ++ci) {
+        const int i = M.child_list[ci];
+        float dGi[4], Ri[9];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dGi[e] = sm[L::DG + (i * 12 + r * 4 + e) * S + s];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Ri[e] = sm[L::RM + (i * 9 + e) * S + s];
+        const float t0 = sm[L::DG + (i * 12 + 3) * S + s], t1 = sm[L::DG + (i * 12 + 7) * S + s], t2 = sm[L::DG + (i * 12 + 11) * S + s];
+        const float rel[3] = {sm[L::JR + (3 * i + 0) * S + s] - Jpx, sm[L::JR + (3 * i + 1) * S + s] - Jpy,
+                              sm[L::JR + (3 * i + 2) * S + s] - Jpz};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            dGp[c] += dGi[0] * Ri[c * 3 + 0] + dGi[1] * Ri[c * 3 + 1] + dGi[2] * Ri[c * 3 + 2] + dGi[3] * rel[c];
+        dGp[3] += dGi[3];
+        dJp -= Gp[0] * t0 + Gp[1] * t1 + Gp[2] * t2;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sm[L::DG + (p * 12 + r * 4 + e) * S + s] = dGp[e];
+    sm[L::DJ + (3 * p + r) * S + s] = dJp;
 }
 
 template <int S, class L>
 __device__ __forceinline__ void ph_chain_backward_rows(const ChainTree& M, float* sm, const Grp g) {
-    for (int lev = M.num_levels - 2; lev >= 0; --lev) {
-        const int first = M.level_start[lev], cnt = M.level_start[lev + 1] - first;
-        FOR_ITEMS_G(it, cnt * 3 * S, g) {
-            const int s = it % S, r = (it / S) % 3, p = M.level_order[first + it / (3 * S)];
-            const int c0 = M.child_start[p], c1 = M.child_start[p + 1];
-            if (c0 == c1) continue;
-            float dGp[4], Gp[3];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dGp[e] = sm[L::DG + (p * 12 + r * 4 + e) * S + s];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) Gp[k] = sm[L::GW + (p * 12 + k * 4 + r) * S + s];            // column r of G_p^R
-            float dJp = sm[L::DJ + (3 * p + r) * S + s];
-            const float Jpx = sm[L::JR + (3 * p + 0) * S + s], Jpy = sm[L::JR + (3 * p + 1) * S + s], Jpz = sm[L::JR + (3 * p + 2) * S + s];
-            for (int ci = c0; ci < c1; ++ci) {
-                const int i = M.child_list[ci];
-                float dGi[4], Ri[9];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) dGi[e] = sm[L::DG + (i * 12 + r * 4 + e) * S + s];
-#pragma unroll
-                for (int e = 0; e < 9; ++e) Ri[e] = sm[L::RM + (i * 9 + e) * S + s];
-                const float t0 = sm[L::DG + (i * 12 + 3) * S + s], t1 = sm[L::DG + (i * 12 + 7) * S + s], t2 = sm[L::DG + (i * 12 + 11) * S + s];
-                const float rel[3] = {sm[L::JR + (3 * i + 0) * S + s] - Jpx, sm[L::JR + (3 * i + 1) * S + s] - Jpy,
-                                      sm[L::JR + (3 * i + 2) * S + s] - Jpz};
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    dGp[c] += dGi[0] * Ri[c * 3 + 0] + dGi[1] * Ri[c * 3 + 1] + dGi[2] * Ri[c * 3 + 2] + dGi[3] * rel[c];
-                dGp[3] += dGi[3];
-                dJp -= Gp[0] * t0 + Gp[1] * t1 + Gp[2] * t2;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) sm[L::DG + (p * 12 + r * 4 + e) * S + s] = dGp[e];
-            sm[L::DJ + (3 * p + r) * S + s] = dJp;
+    const int levels = M.num_levels, s = g.tid % S, r = (g.tid / S) % 3, slot = g.tid / (3 * S);
+    if (levels < 2) return;
+    int first = M.level_start[levels - 2], cnt = M.level_start[levels - 1] - first;
+    int p0 = -1, c0 = 0, c1 = 0;
+    if (slot < cnt) { p0 = M.level_order[first + slot]; c0 = M.child_start[p0]; c1 = M.child_start[p0 + 1]; }
+    for (int lev = levels - 2; lev >= 0; --lev) {
+        int nfirst = 0, ncnt = 0, np = -1, nc0 = 0, nc1 = 0;
+        if (lev > 0) {
+            nfirst = M.level_start[lev - 1];
+            ncnt = M.level_start[lev] - nfirst;
+            if (slot < ncnt) { np = M.level_order[nfirst + slot]; nc0 = M.child_start[np]; nc1 = M.child_start[np + 1]; }
+        }
+        if (p0 >= 0 && c0 != c1) chain_backward_row<S, L>(M, sm, p0, c0, c1, r, s);
+        for (int it = g.tid + g.nt; it < cnt * 3 * S; it += g.nt) {
+            const int p = M.level_order[first + it / (3 * S)], a = M.child_start[p], b = M.child_start[p + 1];
+            if (a != b) chain_backward_row<S, L>(M, sm, p, a, b, (it / S) % 3, it % S);
         }
         grp_sync(g);
+        first = nfirst; cnt = ncnt; p0 = np; c0 = nc0; c1 = nc1;
     }
 }
 // ... and its per-joint tail (dL/dR_j over RM, rest-joint gradient), independent of the tree order: the whole tile runs it
